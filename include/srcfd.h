@@ -1,0 +1,133 @@
+/*
+ * srcfd.h -- C ABI of libsrcfd.so: the B200 (sm_100a) implementation of the fine-grid
+ * Navier-Stokes hot path of bitseal02/SR-for-CFD.
+ *
+ * The reference has no FFI of its own: its "operator interface" is the set of module-level
+ * numba kernels and the CFDSolver methods of PyCFD_ML_accelerated.py (LDC.py below) and
+ * bfs_ml_accelerated.py (BFS.py).  Every entry point here names the reference function it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns 0 on success, non-zero on failure, and
+ *     srcfd_last_error() returns a message for the calling thread's last failure;
+ *   - the caller owns all host buffers; the library owns device state behind the handle;
+ *   - one handle = one flow case on one CUDA device with its own stream; handles are not
+ *     thread-safe, distinct handles may be driven from distinct threads;
+ *   - host arrays use the reference layout: Var/VarOld (3, nx+2, ny+2), Ff (4, nx+2, ny+2),
+ *     float64, C order (j fastest), k = 0:u 1:v 2:p, f = 0:E 1:N 2:W 3:S (LDC.py:342-345);
+ *   - there is no CPU fallback: without a CUDA device srcfd_create fails.
+ */
+#ifndef SRCFD_H
+#define SRCFD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRCFD_ABI_VERSION 1
+
+enum { SRCFD_SCHEME_UPWIND = 0, SRCFD_SCHEME_QUICK = 1 };           /* SolverSettings.scheme, LDC.py:95 */
+enum {
+    SRCFD_ORDER_GS_LEX = 0,   /* reference order: in-place lexicographic Gauss-Seidel (numba, 1 thread),  */
+                              /* run as a pipelined wavefront -- results bit-identical to the reference  */
+    SRCFD_ORDER_JACOBI = 1,   /* every cell from the previous iterate                                     */
+    SRCFD_ORDER_RED_BLACK = 2 /* in-place two-colour sweep                                                */
+};
+enum { SRCFD_BC_DIRICHLET = 0, SRCFD_BC_NEUMANN = 1 };              /* _get_bc_arrays, LDC.py:351-375   */
+
+typedef struct srcfd_params {
+    int32_t nx, ny;              /* MeshParameters, LDC.py:69-78                                   */
+    double  dx, dy, volp;        /*   dx = lx/nx, dy = ly/ny, volp = dx*dy (computed by the caller) */
+    double  dt;                  /* SolverSettings.dt                                               */
+    double  nu, rho;             /* FluidProperties: nu = 1/Re, LDC.py:80-86                        */
+    int32_t scheme;              /* SRCFD_SCHEME_*                                                  */
+    int32_t bc_types[3][4];      /* [k][left,right,top,bottom], SRCFD_BC_*                          */
+    double  bc_values[3][4];
+    int32_t bfs_enabled;         /* CFDSolver.case_type == 'BFS': _apply_bfs_inlet, BFS.py:524-569   */
+    double  bfs_step_h, bfs_h, bfs_Ub;
+    int32_t relax_enabled;       /* under_relax_field calls of BFS.py:643-659                        */
+    double  relax[3];            /*   alpha_u, alpha_v, alpha_p                                      */
+    double  inner_tol;           /* 1e-6, hard-coded at LDC.py:250,272,294                           */
+    int32_t inner_max;           /* 1000, hard-coded at LDC.py:251,273,295                           */
+    int32_t sweep_order;         /* SRCFD_ORDER_*                                                    */
+    int32_t device;              /* CUDA device ordinal                                              */
+    int32_t max_ctas;            /* 0 = whole GPU; >0 caps the persistent grids (ensemble members)   */
+    int32_t reserved[8];
+} srcfd_params;
+
+typedef struct srcfd_handle srcfd_handle;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+int srcfd_abi_version(void);
+const char *srcfd_last_error(void);
+int srcfd_device_count(int *count);
+/* CFDSolver.__init__ (LDC.py:333-349 / BFS.py:473-496) without _initialize_fields: device arrays are zero. */
+int srcfd_create(const srcfd_params *params, srcfd_handle **out);
+int srcfd_destroy(srcfd_handle *h);
+/* Change everything except nx, ny, device (the reference mutates bc / case_type after construction). */
+int srcfd_set_params(srcfd_handle *h, const srcfd_params *params);
+int srcfd_synchronize(srcfd_handle *h);
+/* The CUDA stream (cudaStream_t as an integer) the handle launches on. */
+int srcfd_stream(srcfd_handle *h, uint64_t *stream);
+
+/* ---- state transfer (any pointer may be NULL = skip) --------------------------------------- */
+int srcfd_upload(srcfd_handle *h, const double *Var, const double *VarOld, const double *Ff, const double *residual);
+int srcfd_download(srcfd_handle *h, double *Var, double *VarOld, double *Ff, double *residual);
+/* Device addresses of the state arrays, for callers that keep inputs resident in HBM. */
+int srcfd_device_ptrs(srcfd_handle *h, uint64_t *Var, uint64_t *VarOld, uint64_t *Ff);
+
+/* ---- composed path ------------------------------------------------------------------------- */
+/* _initialize_fields (LDC.py:377-389): optional zero fill, BC on u,v,p, copy_new_to_old, linear_interpolation. */
+int srcfd_initialize_fields(srcfd_handle *h, int zero_first);
+/* Warm-start injection (LDC.py:936-948): fields = (3, ny, nx) float64 or float32 on the host; writes
+ * Var[k,1:-1,1:-1] = fields[k].T, then BC x3, copy_new_to_old, linear_interpolation. */
+int srcfd_set_fields(srcfd_handle *h, const void *fields, int is_float32);
+/* Enqueue n_outer x (_implicit_solve + _convergence_check) (LDC.py:408-419, 432-501) with no host
+ * round trip; iterations after convergence / NaN are skipped on the device.  crit = {u, v, p}. */
+int srcfd_step(srcfd_handle *h, int64_t n_outer, const double crit[3]);
+/* Wait for enqueued work and report: iterations done since the last srcfd_reset_counters, converged
+ * flag, last rms triplet (sqrt(res/(nx*ny))/dt), last inner sweep counts, cumulative inner sweeps.
+ * Returns SRCFD_ERR_NAN (3) when the reference would raise ValueError("Solver failed: NaN/Inf in residuals"). */
+int srcfd_status(srcfd_handle *h, int64_t *iterations, int32_t *converged, double rms[3],
+                 int32_t last_sweeps[3], int64_t total_sweeps[3]);
+int srcfd_reset_counters(srcfd_handle *h);
+/* CFDSolver.solve loop (LDC.py:396-430) without printing/saving: runs until converged or max_iterations.
+ * hist receives the rms triplets sampled when count % 100 == 0 (at most hist_cap triplets). */
+int srcfd_solve(srcfd_handle *h, int64_t max_iterations, const double crit[3], int64_t *iterations,
+                double *seconds, double *hist, int64_t hist_cap, int64_t *n_hist);
+
+/* ---- kernel-level entry points, one per reference kernel, on the handle's device arrays ---- */
+int srcfd_k_copy_new_to_old(srcfd_handle *h);                         /* LDC.py:110-115 */
+int srcfd_k_apply_bc(srcfd_handle *h, int k);                         /* _apply_bc_wrapper: LDC.py:391-394, BFS.py:564-569 */
+int srcfd_k_apply_bc_configured(srcfd_handle *h, int k);              /* apply_bc_configured alone: LDC.py:117-145 */
+int srcfd_k_apply_bfs_inlet(srcfd_handle *h, int k);                  /* _apply_bfs_inlet alone: BFS.py:524-562 */
+int srcfd_k_linear_interpolation(srcfd_handle *h);                    /* LDC.py:147-154 */
+int srcfd_k_update_flux(srcfd_handle *h);                             /* LDC.py:239-246 */
+int srcfd_k_under_relax(srcfd_handle *h, int k, double alpha);        /* BFS.py:371-375 */
+int srcfd_k_correct_velocity(srcfd_handle *h, double residual_out[3]);/* LDC.py:316-328 (residual += sums) */
+int srcfd_k_solve_pressure(srcfd_handle *h, int32_t *sweeps, double *last_rms);          /* LDC.py:292-314 */
+int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, double *last_rms); /* LDC.py:248-290 */
+/* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
+int srcfd_k_implicit_solve(srcfd_handle *h);
+
+/* ---- introspection for benchmarks ---------------------------------------------------------- */
+/* Number of kernels this library has launched on the handle's stream since creation. */
+int srcfd_launch_count(srcfd_handle *h, int64_t *launches);
+/* Device time (ms) and launches of the inner-solve kernels accumulated while timing is enabled
+ * (CUDA events recorded around every inner-solve launch on the handle's stream). */
+int srcfd_timing_enable(srcfd_handle *h, int enabled);
+int srcfd_timing_read(srcfd_handle *h, double *pressure_ms, int64_t *pressure_launches,
+                      double *momentum_ms, int64_t *momentum_launches);
+
+#define SRCFD_OK 0
+#define SRCFD_ERR_ARG 1
+#define SRCFD_ERR_CUDA 2
+#define SRCFD_ERR_NAN 3
+#define SRCFD_ERR_DEADLOCK 4
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRCFD_H */

@@ -1,0 +1,601 @@
+// srcfd.cu -- C ABI (include/srcfd.h) over the sm_100a kernels.  Single translation unit.
+// Build: see sr-for-cfd_b200/csrc/Makefile (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/srcfd.h"
+#include "common.cuh"
+#include "cell_ops.cuh"
+#include "tail_kernels.cuh"
+#include "inner_solvers.cuh"
+
+using namespace srcfd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SRCFD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+#define CKH(h)                                                                                     \
+    do {                                                                                           \
+        if (!(h)) return fail(SRCFD_ERR_ARG, "null handle");                                       \
+        CK(cudaSetDevice((h)->dev));                                                               \
+    } while (0)
+
+struct EvPair { cudaEvent_t a, b; int kind; };
+
+struct srcfd_handle {
+    srcfd_params p;
+    Consts K;
+    BcSpec bc;
+    int dev = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    double *Var = nullptr, *VarOld = nullptr, *Ff = nullptr, *rhs = nullptr, *scratch = nullptr;
+    double *partials = nullptr, *res_partials = nullptr, *hist = nullptr;
+    void* staging = nullptr;
+    size_t staging_bytes = 0;
+    int* prog = nullptr;
+    Ctrl* ctrl = nullptr;       // device
+    Ctrl* ctrl_host = nullptr;  // pinned mirror
+    long long hist_cap = 0;
+    int nbands = 1, band_rows = 1, wf_threads = 32;
+    int grid_gs[3] = {0, 0, 0}, grid_sync = 0, tail_blocks = 0;
+    size_t wf_smem = 0;
+    size_t n_partials = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<EvPair> ev_pending, ev_free;
+    double t_ms[2] = {0, 0};
+    int64_t t_n[2] = {0, 0};
+    int spin_limit = 4000000;
+    int inner_cap = 0;          // capacity of the per-sweep buffers (inner_max at creation)
+    int guess_bias = 0;
+};
+
+// Derived constants, each with the reference's own expression (host compiled with -ffp-contract=off).
+static Consts make_consts(const srcfd_params& p) {
+    Consts K;
+    K.nx = p.nx; K.ny = p.ny; K.pitch = p.ny + 2; K.plane = (long long)(p.nx + 2) * (p.ny + 2);
+    K.dx = p.dx; K.dy = p.dy; K.volp = p.volp; K.dt = p.dt; K.nu = p.nu; K.rho = p.rho;
+    K.dx2 = p.dx * p.dx; K.dy2 = p.dy * p.dy;
+    K.ap_d = -p.volp * (2.0 / (p.dx * p.dx) + 2.0 / (p.dy * p.dy));
+    K.volp_dt = p.volp / p.dt;
+    K.rho_dt = p.rho / p.dt;
+    K.neg_nu = -p.nu;
+    K.neg_nu_ap_d = (-p.nu) * K.ap_d;
+    K.dt_rho = p.dt / p.rho;
+    K.mdt_rho = -p.dt / p.rho;
+    K.two_dx = 2 * p.dx; K.two_dy = 2 * p.dy;
+    return K;
+}
+static BcSpec make_bc(const srcfd_params& p) {
+    BcSpec b;
+    for (int k = 0; k < 3; ++k)
+        for (int s = 0; s < 4; ++s) { b.types[k][s] = p.bc_types[k][s]; b.values[k][s] = p.bc_values[k][s]; }
+    b.bfs = p.bfs_enabled; b.step_h = p.bfs_step_h; b.h = p.bfs_h; b.Ub = p.bfs_Ub;
+    return b;
+}
+
+static int check_params(const srcfd_params* p) {
+    if (!p) return fail(SRCFD_ERR_ARG, "null params");
+    if (p->nx < 1 || p->ny < 1) return fail(SRCFD_ERR_ARG, "nx, ny must be >= 1");
+    if (p->scheme != SRCFD_SCHEME_UPWIND && p->scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
+    if (p->sweep_order < 0 || p->sweep_order > 2) return fail(SRCFD_ERR_ARG, "bad sweep_order");
+    if (p->inner_max < 1) return fail(SRCFD_ERR_ARG, "inner_max must be >= 1");
+    if (p->sweep_order == SRCFD_ORDER_RED_BLACK && p->scheme == SRCFD_SCHEME_QUICK)
+        return fail(SRCFD_ERR_ARG, "red-black order is undefined for the 9-point QUICK stencil (same-colour second neighbours)");
+    return SRCFD_OK;
+}
+
+template <int OP> static const void* gs_kernel() { return (const void*)k_solve_gs<OP>; }
+template <int OP, int ORDER> static const void* sync_kernel() { return (const void*)k_solve_sync<OP, ORDER>; }
+
+static const void* pick_sync(int op, int order) {
+    if (order == SRCFD_ORDER_JACOBI) {
+        if (op == OP_PRESSURE) return sync_kernel<OP_PRESSURE, 1>();
+        if (op == OP_UPWIND) return sync_kernel<OP_UPWIND, 1>();
+        return sync_kernel<OP_QUICK, 1>();
+    }
+    if (op == OP_PRESSURE) return sync_kernel<OP_PRESSURE, 2>();
+    return sync_kernel<OP_UPWIND, 2>();
+}
+static const void* pick_gs(int op) {
+    if (op == OP_PRESSURE) return gs_kernel<OP_PRESSURE>();
+    if (op == OP_UPWIND) return gs_kernel<OP_UPWIND>();
+    return gs_kernel<OP_QUICK>();
+}
+
+static int plan_launches(srcfd_handle* h) {
+    const int nx = h->p.nx;
+    h->nbands = (nx + WF_MAX_BAND - 1) / WF_MAX_BAND;
+    h->band_rows = (nx + h->nbands - 1) / h->nbands;
+    h->nbands = (nx + h->band_rows - 1) / h->band_rows;
+    h->wf_threads = ((h->band_rows + 4 + 31) / 32) * 32;
+    h->wf_smem = sizeof(double) * (8 * (size_t)(h->wf_threads + 4) + 4 + 32);
+    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+    for (int op = 0; op < 3; ++op) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_gs(op), h->wf_threads, h->wf_smem));
+        if (occ < 1) return fail(SRCFD_ERR_CUDA, "wavefront kernel does not fit on an SM");
+        h->grid_gs[op] = std::max(1, std::min(cap, occ * h->num_sms));
+    }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_sync(OP_QUICK, SRCFD_ORDER_JACOBI), SYNC_THREADS, 0));
+    if (occ < 1) return fail(SRCFD_ERR_CUDA, "sync kernel does not fit on an SM");
+    const long long ncell = (long long)h->p.nx * h->p.ny;
+    const long long want = (ncell + SYNC_THREADS - 1) / SYNC_THREADS;
+    h->grid_sync = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(cap, (long long)occ * h->num_sms), want));
+    h->tail_blocks = (int)want;
+    return SRCFD_OK;
+}
+
+extern "C" {
+
+int srcfd_abi_version(void) { return SRCFD_ABI_VERSION; }
+const char* srcfd_last_error(void) { return g_err.c_str(); }
+
+int srcfd_device_count(int* count) {
+    if (!count) return fail(SRCFD_ERR_ARG, "null count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return fail(SRCFD_ERR_CUDA, cudaGetErrorString(e)); }
+    return SRCFD_OK;
+}
+
+int srcfd_destroy(srcfd_handle* h) {
+    if (!h) return SRCFD_OK;
+    cudaSetDevice(h->dev);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& e : h->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : h->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
+    cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
+    cudaFree(h->staging);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SRCFD_OK;
+}
+
+int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
+    if (!out) return fail(SRCFD_ERR_ARG, "null out");
+    *out = nullptr;
+    if (int rc = check_params(params)) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SRCFD_ERR_CUDA, "no CUDA device: libsrcfd has no CPU fallback");
+    if (params->device < 0 || params->device >= ndev) return fail(SRCFD_ERR_ARG, "bad device ordinal");
+    srcfd_handle* h = new srcfd_handle();
+    h->p = *params; h->K = make_consts(*params); h->bc = make_bc(*params); h->dev = params->device;
+    h->inner_cap = params->inner_max;
+    auto bail = [&](int rc) { std::string keep = g_err; srcfd_destroy(h); g_err = keep; return rc; };
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(SRCFD_ERR_CUDA); } } while (0)
+    CKB(cudaSetDevice(h->dev));
+    cudaDeviceProp prop;
+    CKB(cudaGetDeviceProperties(&prop, h->dev));
+    if (!prop.cooperativeLaunch) { g_err = "device lacks cooperative launch"; return bail(SRCFD_ERR_CUDA); }
+    h->num_sms = prop.multiProcessorCount;
+    CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (const char* s = getenv("SRCFD_SPIN_LIMIT")) h->spin_limit = atoi(s);
+    if (const char* s = getenv("SRCFD_GUESS_BIAS")) h->guess_bias = atoi(s);
+    if (int rc = plan_launches(h)) return bail(rc);
+    const size_t P = (size_t)h->K.plane;
+    const size_t pad = 4 * (size_t)h->K.pitch + 64;   // QUICK's flat over-reads stay inside the allocation
+    CKB(cudaMalloc(&h->Var, sizeof(double) * (3 * P + pad)));
+    CKB(cudaMalloc(&h->VarOld, sizeof(double) * (3 * P + pad)));
+    CKB(cudaMalloc(&h->Ff, sizeof(double) * (4 * P + pad)));
+    CKB(cudaMalloc(&h->rhs, sizeof(double) * (P + pad)));
+    CKB(cudaMalloc(&h->scratch, sizeof(double) * (P + pad)));
+    int gmax = std::max(h->grid_sync, std::max(h->grid_gs[0], std::max(h->grid_gs[1], h->grid_gs[2])));
+    h->n_partials = std::max((size_t)h->inner_cap * h->nbands, (size_t)2 * gmax) + 64;
+    CKB(cudaMalloc(&h->partials, sizeof(double) * h->n_partials));
+    CKB(cudaMalloc(&h->prog, sizeof(int) * ((size_t)h->inner_cap * h->nbands + 64)));
+    CKB(cudaMalloc(&h->res_partials, sizeof(double) * 3 * (size_t)(h->tail_blocks + 1)));
+    CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
+    CKB(cudaMallocHost(&h->ctrl_host, sizeof(Ctrl)));
+    CKB(cudaMemsetAsync(h->Var, 0, sizeof(double) * (3 * P + pad), h->stream));
+    CKB(cudaMemsetAsync(h->VarOld, 0, sizeof(double) * (3 * P + pad), h->stream));
+    CKB(cudaMemsetAsync(h->Ff, 0, sizeof(double) * (4 * P + pad), h->stream));
+    CKB(cudaMemsetAsync(h->rhs, 0, sizeof(double) * (P + pad), h->stream));
+    CKB(cudaMemsetAsync(h->scratch, 0, sizeof(double) * (P + pad), h->stream));
+    CKB(cudaMemsetAsync(h->prog, 0, sizeof(int) * ((size_t)h->inner_cap * h->nbands + 64), h->stream));
+    memset(h->ctrl_host, 0, sizeof(Ctrl));
+    h->ctrl_host->guess[0] = h->ctrl_host->guess[1] = std::min(8, h->p.inner_max);
+    h->ctrl_host->guess[2] = h->p.inner_max;
+    CKB(cudaMemcpyAsync(h->ctrl, h->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+    CKB(cudaStreamSynchronize(h->stream));
+#undef CKB
+    *out = h;
+    return SRCFD_OK;
+}
+
+int srcfd_set_params(srcfd_handle* h, const srcfd_params* params) {
+    CKH(h);
+    if (int rc = check_params(params)) return rc;
+    if (params->nx != h->p.nx || params->ny != h->p.ny || params->device != h->p.device)
+        return fail(SRCFD_ERR_ARG, "nx, ny and device are fixed at creation");
+    if (params->inner_max > h->inner_cap) return fail(SRCFD_ERR_ARG, "inner_max cannot exceed its value at creation");
+    const int keep_ctas = h->p.max_ctas;
+    h->p = *params; h->p.max_ctas = keep_ctas;
+    h->K = make_consts(*params); h->bc = make_bc(*params);
+    return SRCFD_OK;
+}
+
+int srcfd_synchronize(srcfd_handle* h) { CKH(h); CK(cudaStreamSynchronize(h->stream)); return SRCFD_OK; }
+int srcfd_stream(srcfd_handle* h, uint64_t* stream) {
+    CKH(h);
+    if (!stream) return fail(SRCFD_ERR_ARG, "null stream out");
+    *stream = (uint64_t)(uintptr_t)h->stream;
+    return SRCFD_OK;
+}
+
+int srcfd_upload(srcfd_handle* h, const double* Var, const double* VarOld, const double* Ff, const double* residual) {
+    CKH(h);
+    const size_t P = (size_t)h->K.plane;
+    if (Var) CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
+    if (VarOld) CK(cudaMemcpyAsync(h->VarOld, VarOld, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
+    if (Ff) CK(cudaMemcpyAsync(h->Ff, Ff, sizeof(double) * 4 * P, cudaMemcpyHostToDevice, h->stream));
+    if (residual) CK(cudaMemcpyAsync((char*)h->ctrl + offsetof(Ctrl, residual), residual, sizeof(double) * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // host buffers may be pageable and reused by the caller
+    return SRCFD_OK;
+}
+
+int srcfd_download(srcfd_handle* h, double* Var, double* VarOld, double* Ff, double* residual) {
+    CKH(h);
+    const size_t P = (size_t)h->K.plane;
+    if (Var) CK(cudaMemcpyAsync(Var, h->Var, sizeof(double) * 3 * P, cudaMemcpyDeviceToHost, h->stream));
+    if (VarOld) CK(cudaMemcpyAsync(VarOld, h->VarOld, sizeof(double) * 3 * P, cudaMemcpyDeviceToHost, h->stream));
+    if (Ff) CK(cudaMemcpyAsync(Ff, h->Ff, sizeof(double) * 4 * P, cudaMemcpyDeviceToHost, h->stream));
+    if (residual) CK(cudaMemcpyAsync(residual, (char*)h->ctrl + offsetof(Ctrl, residual), sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SRCFD_OK;
+}
+
+int srcfd_device_ptrs(srcfd_handle* h, uint64_t* Var, uint64_t* VarOld, uint64_t* Ff) {
+    CKH(h);
+    if (Var) *Var = (uint64_t)(uintptr_t)h->Var;
+    if (VarOld) *VarOld = (uint64_t)(uintptr_t)h->VarOld;
+    if (Ff) *Ff = (uint64_t)(uintptr_t)h->Ff;
+    return SRCFD_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers (C++ linkage)
+// ------------------------------------------------------------------------------------------------
+#define LAUNCH_CHECK(h)                                                                            \
+    do {                                                                                           \
+        (h)->launches += 1;                                                                        \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess) return fail(SRCFD_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+static int l_copy_new_to_old(srcfd_handle* h) {
+    const long long n = 3 * h->K.plane;
+    const int blocks = (int)std::min<long long>((n + TAIL_THREADS - 1) / TAIL_THREADS, (long long)h->num_sms * 8);
+    k_copy_new_to_old<<<blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, n, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_apply_bc(srcfd_handle* h, int k, int mode = 0) {
+    const int n = std::max(h->K.nx, h->K.ny);
+    k_apply_bc<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Var, k, h->K, h->bc, mode, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_linear_interpolation(srcfd_handle* h, bool with_rhs) {
+    k_linear_interpolation<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->Ff, with_rhs ? h->rhs : nullptr, h->K, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_pressure_rhs(srcfd_handle* h) {
+    k_pressure_rhs<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Ff, h->rhs, h->K, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_update_flux(srcfd_handle* h) {
+    k_update_flux<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->Ff, h->K, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_under_relax(srcfd_handle* h, int k, double alpha) {
+    k_under_relax<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, k, alpha, h->K, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_correct_velocity(srcfd_handle* h) {
+    k_correct_velocity<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, h->res_partials, h->K, h->ctrl);
+    LAUNCH_CHECK(h);
+    k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_zero_residual(srcfd_handle* h) {
+    k_zero_residual<<<1, 1, 0, h->stream>>>(h->ctrl);
+    LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+
+static int ev_begin(srcfd_handle* h, int kind, EvPair& ev) {
+    if (h->ev_free.empty()) {
+        CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+    } else { ev = h->ev_free.back(); h->ev_free.pop_back(); }
+    ev.kind = kind;
+    CK(cudaEventRecord(ev.a, h->stream));
+    return SRCFD_OK;
+}
+static int ev_end(srcfd_handle* h, EvPair& ev) {
+    CK(cudaEventRecord(ev.b, h->stream));
+    h->ev_pending.push_back(ev);
+    return SRCFD_OK;
+}
+static int ev_drain(srcfd_handle* h) {
+    for (auto& ev : h->ev_pending) {
+        CK(cudaEventSynchronize(ev.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        h->t_ms[ev.kind] += ms; h->t_n[ev.kind] += 1;
+        h->ev_free.push_back(ev);
+    }
+    h->ev_pending.clear();
+    return SRCFD_OK;
+}
+
+// One inner solve: op in {OP_PRESSURE, OP_UPWIND, OP_QUICK} on plane k, counters in slot.
+static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
+    SolveArgs a;
+    a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
+    a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
+    a.k = k; a.slot = slot; a.tol = h->p.inner_tol; a.max_iter = h->p.inner_max;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = h->guess_bias;
+    void* args[] = {&a};
+    EvPair ev;
+    if (h->timing) if (int rc = ev_begin(h, op == OP_PRESSURE ? 0 : 1, ev)) return rc;
+    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
+        CK(cudaLaunchCooperativeKernel(pick_gs(op), dim3(h->grid_gs[op]), dim3(h->wf_threads), args, h->wf_smem, h->stream));
+    } else {
+        if (h->p.sweep_order == SRCFD_ORDER_RED_BLACK && op == OP_QUICK)
+            return fail(SRCFD_ERR_ARG, "red-black order is undefined for QUICK");
+        CK(cudaLaunchCooperativeKernel(pick_sync(op, h->p.sweep_order), dim3(h->grid_sync), dim3(SYNC_THREADS), args, 0, h->stream));
+    }
+    h->launches += 1;
+    if (h->timing) if (int rc = ev_end(h, ev)) return rc;
+    return SRCFD_OK;
+}
+
+#define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
+
+// _implicit_solve: LDC.py:432-467 / BFS.py:622-673
+static int l_implicit_solve(srcfd_handle* h) {
+    TRY(l_zero_residual(h));
+    const int mop = h->p.scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND;
+    for (int k = 0; k < 2; ++k) {
+        TRY(l_inner_solve(h, mop, k, k));
+        if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));
+        TRY(l_apply_bc(h, k));
+    }
+    TRY(l_linear_interpolation(h, true));
+    TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
+    if (h->p.relax_enabled) TRY(l_under_relax(h, 2, h->p.relax[2]));
+    TRY(l_apply_bc(h, 2));
+    TRY(l_correct_velocity(h));
+    TRY(l_apply_bc(h, 0));
+    TRY(l_apply_bc(h, 1));
+    TRY(l_update_flux(h));
+    return SRCFD_OK;
+}
+
+static int fetch_ctrl(srcfd_handle* h) {
+    CK(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SRCFD_OK;
+}
+static int push_ctrl(srcfd_handle* h) {
+    CK(cudaMemcpyAsync(h->ctrl, h->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SRCFD_OK;
+}
+static int ctrl_verdict(srcfd_handle* h) {
+    if (h->ctrl_host->deadlock) return fail(SRCFD_ERR_DEADLOCK, "wavefront dependence wait exceeded its spin limit");
+    if (h->ctrl_host->nan_flag) return fail(SRCFD_ERR_NAN, "Solver failed: NaN/Inf in residuals");
+    return SRCFD_OK;
+}
+
+extern "C" {
+
+int srcfd_initialize_fields(srcfd_handle* h, int zero_first) {
+    CKH(h);
+    const size_t P = (size_t)h->K.plane;
+    if (zero_first) {
+        CK(cudaMemsetAsync(h->Var, 0, sizeof(double) * 3 * P, h->stream));
+        CK(cudaMemsetAsync(h->VarOld, 0, sizeof(double) * 3 * P, h->stream));
+        CK(cudaMemsetAsync(h->Ff, 0, sizeof(double) * 4 * P, h->stream));
+    }
+    for (int k = 0; k < 3; ++k) TRY(l_apply_bc(h, k));
+    TRY(l_copy_new_to_old(h));
+    TRY(l_linear_interpolation(h, false));
+    return SRCFD_OK;
+}
+
+int srcfd_set_fields(srcfd_handle* h, const void* fields, int is_float32) {
+    CKH(h);
+    if (!fields) return fail(SRCFD_ERR_ARG, "null fields");
+    const size_t n = 3 * (size_t)h->K.nx * h->K.ny;
+    const size_t bytes = n * (is_float32 ? sizeof(float) : sizeof(double));
+    if (h->staging_bytes < bytes) {
+        cudaFree(h->staging); h->staging = nullptr; h->staging_bytes = 0;
+        CK(cudaMalloc(&h->staging, bytes));
+        h->staging_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(h->staging, fields, bytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((h->K.nx + 31) / 32, (h->K.ny + 31) / 32, 3), block(32, 8);
+    if (is_float32) k_inject_fields<float><<<grid, block, 0, h->stream>>>(h->Var, (const float*)h->staging, h->K);
+    else k_inject_fields<double><<<grid, block, 0, h->stream>>>(h->Var, (const double*)h->staging, h->K);
+    LAUNCH_CHECK(h);
+    TRY(srcfd_initialize_fields(h, 0));
+    CK(cudaStreamSynchronize(h->stream));
+    return SRCFD_OK;
+}
+
+int srcfd_step(srcfd_handle* h, int64_t n_outer, const double crit[3]) {
+    CKH(h);
+    if (!crit) return fail(SRCFD_ERR_ARG, "null crit");
+    for (int64_t it = 0; it < n_outer; ++it) {
+        TRY(l_implicit_solve(h));
+        k_convergence_check<<<1, 1, 0, h->stream>>>(h->ctrl, h->hist, h->K, crit[0], crit[1], crit[2]);
+        LAUNCH_CHECK(h);
+        TRY(l_copy_new_to_old(h));
+    }
+    return SRCFD_OK;
+}
+
+int srcfd_status(srcfd_handle* h, int64_t* iterations, int32_t* converged, double rms[3],
+                 int32_t last_sweeps[3], int64_t total_sweeps[3]) {
+    CKH(h);
+    TRY(fetch_ctrl(h));
+    if (h->timing) TRY(ev_drain(h));
+    const Ctrl& c = *h->ctrl_host;
+    if (iterations) *iterations = c.iterations;
+    if (converged) *converged = c.converged;
+    for (int k = 0; k < 3; ++k) {
+        if (rms) rms[k] = c.rms[k];
+        if (last_sweeps) last_sweeps[k] = c.last_sweeps[k];
+        if (total_sweeps) total_sweeps[k] = c.total_sweeps[k];
+    }
+    return ctrl_verdict(h);
+}
+
+int srcfd_reset_counters(srcfd_handle* h) {
+    CKH(h);
+    TRY(fetch_ctrl(h));
+    Ctrl& c = *h->ctrl_host;
+    c.stop = c.converged = c.nan_flag = c.deadlock = 0;
+    c.iterations = 0; c.n_hist = 0;
+    for (int k = 0; k < 3; ++k) { c.total_sweeps[k] = 0; c.last_sweeps[k] = 0; }
+    return push_ctrl(h);
+}
+
+int srcfd_solve(srcfd_handle* h, int64_t max_iterations, const double crit[3], int64_t* iterations,
+                double* seconds, double* hist, int64_t hist_cap, int64_t* n_hist) {
+    CKH(h);
+    if (!crit) return fail(SRCFD_ERR_ARG, "null crit");
+    auto t0 = std::chrono::steady_clock::now();
+    TRY(srcfd_reset_counters(h));
+    const long long want_hist = max_iterations / 100 + 1;
+    if (h->hist_cap < want_hist) {
+        cudaFree(h->hist); h->hist = nullptr; h->hist_cap = 0;
+        CK(cudaMalloc(&h->hist, sizeof(double) * 3 * want_hist));
+        h->hist_cap = want_hist;
+    }
+    h->ctrl_host->hist_cap = h->hist_cap;
+    TRY(push_ctrl(h));
+    int64_t enq = 0;
+    int rc = SRCFD_OK;
+    while (enq < max_iterations) {
+        const int64_t chunk = std::min<int64_t>(25, max_iterations - enq);
+        TRY(srcfd_step(h, chunk, crit));
+        enq += chunk;
+        TRY(fetch_ctrl(h));
+        rc = ctrl_verdict(h);
+        if (rc || h->ctrl_host->stop) break;
+    }
+    if (h->timing) TRY(ev_drain(h));
+    const Ctrl& c = *h->ctrl_host;
+    if (iterations) *iterations = c.iterations;
+    const int64_t nh = std::min<int64_t>(c.n_hist, hist_cap);
+    if (hist && nh > 0) {
+        CK(cudaMemcpyAsync(hist, h->hist, sizeof(double) * 3 * nh, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (n_hist) *n_hist = hist ? nh : 0;
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+// ---- kernel-level entry points ----------------------------------------------------------------
+int srcfd_k_copy_new_to_old(srcfd_handle* h) { CKH(h); return l_copy_new_to_old(h); }
+int srcfd_k_apply_bc(srcfd_handle* h, int k) {
+    CKH(h);
+    if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
+    return l_apply_bc(h, k);
+}
+int srcfd_k_apply_bc_configured(srcfd_handle* h, int k) {
+    CKH(h);
+    if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
+    return l_apply_bc(h, k, 1);
+}
+int srcfd_k_apply_bfs_inlet(srcfd_handle* h, int k) {
+    CKH(h);
+    if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
+    return l_apply_bc(h, k, 2);
+}
+int srcfd_k_linear_interpolation(srcfd_handle* h) { CKH(h); return l_linear_interpolation(h, false); }
+int srcfd_k_update_flux(srcfd_handle* h) { CKH(h); return l_update_flux(h); }
+int srcfd_k_under_relax(srcfd_handle* h, int k, double alpha) {
+    CKH(h);
+    if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
+    return l_under_relax(h, k, alpha);
+}
+int srcfd_k_correct_velocity(srcfd_handle* h, double residual_out[3]) {
+    CKH(h);
+    TRY(l_correct_velocity(h));
+    if (residual_out) return srcfd_download(h, nullptr, nullptr, nullptr, residual_out);
+    return SRCFD_OK;
+}
+static int finish_inner(srcfd_handle* h, int slot, int32_t* sweeps, double* last_rms) {
+    TRY(fetch_ctrl(h));
+    if (h->timing) TRY(ev_drain(h));
+    if (sweeps) *sweeps = h->ctrl_host->last_sweeps[slot];
+    if (last_rms) *last_rms = h->ctrl_host->last_inner_rms[slot];
+    return ctrl_verdict(h);
+}
+int srcfd_k_solve_pressure(srcfd_handle* h, int32_t* sweeps, double* last_rms) {
+    CKH(h);
+    TRY(l_pressure_rhs(h));
+    TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
+    return finish_inner(h, 2, sweeps, last_rms);
+}
+int srcfd_k_solve_momentum(srcfd_handle* h, int k, int scheme, int32_t* sweeps, double* last_rms) {
+    CKH(h);
+    if (k < 0 || k > 1) return fail(SRCFD_ERR_ARG, "momentum is solved for k = 0 (u) or 1 (v)");
+    if (scheme != SRCFD_SCHEME_UPWIND && scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
+    TRY(l_inner_solve(h, scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND, k, k));
+    return finish_inner(h, k, sweeps, last_rms);
+}
+int srcfd_k_implicit_solve(srcfd_handle* h) { CKH(h); return l_implicit_solve(h); }
+
+int srcfd_launch_count(srcfd_handle* h, int64_t* launches) {
+    if (!h || !launches) return fail(SRCFD_ERR_ARG, "null argument");
+    *launches = h->launches;
+    return SRCFD_OK;
+}
+int srcfd_timing_enable(srcfd_handle* h, int enabled) {
+    CKH(h);
+    if (h->timing) TRY(ev_drain(h));
+    h->timing = enabled != 0;
+    h->t_ms[0] = h->t_ms[1] = 0; h->t_n[0] = h->t_n[1] = 0;
+    return SRCFD_OK;
+}
+int srcfd_timing_read(srcfd_handle* h, double* pressure_ms, int64_t* pressure_launches, double* momentum_ms,
+                      int64_t* momentum_launches) {
+    CKH(h);
+    TRY(ev_drain(h));
+    if (pressure_ms) *pressure_ms = h->t_ms[0];
+    if (pressure_launches) *pressure_launches = h->t_n[0];
+    if (momentum_ms) *momentum_ms = h->t_ms[1];
+    if (momentum_launches) *momentum_launches = h->t_n[1];
+    return SRCFD_OK;
+}
+
+}  // extern "C"

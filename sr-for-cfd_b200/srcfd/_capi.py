@@ -1,0 +1,232 @@
+"""ctypes binding of libsrcfd.so (include/srcfd.h).  No CPU fallback: if the CUDA library is
+missing or no CUDA device is present, the calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsrcfd.so")
+
+SCHEME_UPWIND, SCHEME_QUICK = 0, 1
+ORDER_GS_LEX, ORDER_JACOBI, ORDER_RED_BLACK = 0, 1, 2
+ORDERS = {"GS_LEX": ORDER_GS_LEX, "REFERENCE": ORDER_GS_LEX, "JACOBI": ORDER_JACOBI, "RED_BLACK": ORDER_RED_BLACK,
+          "RB": ORDER_RED_BLACK}
+OK, ERR_ARG, ERR_CUDA, ERR_NAN, ERR_DEADLOCK = 0, 1, 2, 3, 4
+
+
+class SrcfdError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32),
+        ("dx", C.c_double), ("dy", C.c_double), ("volp", C.c_double),
+        ("dt", C.c_double),
+        ("nu", C.c_double), ("rho", C.c_double),
+        ("scheme", C.c_int32),
+        ("bc_types", (C.c_int32 * 4) * 3),
+        ("bc_values", (C.c_double * 4) * 3),
+        ("bfs_enabled", C.c_int32),
+        ("bfs_step_h", C.c_double), ("bfs_h", C.c_double), ("bfs_Ub", C.c_double),
+        ("relax_enabled", C.c_int32),
+        ("relax", C.c_double * 3),
+        ("inner_tol", C.c_double),
+        ("inner_max", C.c_int32),
+        ("sweep_order", C.c_int32),
+        ("device", C.c_int32),
+        ("max_ctas", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+# every symbol include/srcfd.h declares (tests check that the shared object exports all of them)
+SYMBOLS = [
+    "srcfd_abi_version", "srcfd_last_error", "srcfd_device_count", "srcfd_create", "srcfd_destroy",
+    "srcfd_set_params", "srcfd_synchronize", "srcfd_stream", "srcfd_upload", "srcfd_download",
+    "srcfd_device_ptrs", "srcfd_initialize_fields", "srcfd_set_fields", "srcfd_step", "srcfd_status",
+    "srcfd_reset_counters", "srcfd_solve", "srcfd_k_copy_new_to_old", "srcfd_k_apply_bc",
+    "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
+    "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
+    "srcfd_k_solve_pressure", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
+    "srcfd_timing_enable", "srcfd_timing_read",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C sr-for-cfd_b200/csrc`).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.srcfd_last_error.restype = C.c_char_p
+        for name in SYMBOLS:
+            getattr(L, name)  # AttributeError here = header/library mismatch
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc == OK:
+        return
+    msg = lib().srcfd_last_error().decode("utf8", "replace")
+    if rc == ERR_NAN:
+        raise ValueError("Solver failed: NaN/Inf in residuals")   # PyCFD_ML_accelerated.py:487
+    raise SrcfdError(f"libsrcfd error {rc}: {msg}")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().srcfd_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], \
+        "libsrcfd wants C-contiguous float64 arrays"
+    return a.ctypes.data_as(_dp)
+
+
+class Handle:
+    """Owns one srcfd_handle (one flow case on one device)."""
+
+    def __init__(self, params: Params):
+        self._h = C.c_void_p()
+        self.params = params
+        check(lib().srcfd_create(C.byref(params), C.byref(self._h)))
+        self.nx, self.ny = params.nx, params.ny
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().srcfd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters / transfer
+    def set_params(self, params: Params):
+        check(lib().srcfd_set_params(self._h, C.byref(params)))
+        self.params = params
+
+    def upload(self, Var=None, VarOld=None, Ff=None, residual=None):
+        check(lib().srcfd_upload(self._h, _ptr(Var), _ptr(VarOld), _ptr(Ff), _ptr(residual)))
+
+    def download(self, Var=None, VarOld=None, Ff=None, residual=None):
+        check(lib().srcfd_download(self._h, _ptr(Var), _ptr(VarOld), _ptr(Ff), _ptr(residual)))
+
+    def synchronize(self):
+        check(lib().srcfd_synchronize(self._h))
+
+    def stream(self) -> int:
+        s = C.c_uint64(0)
+        check(lib().srcfd_stream(self._h, C.byref(s)))
+        return s.value
+
+    def device_ptrs(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().srcfd_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ---- composed path
+    def initialize_fields(self, zero_first=True):
+        check(lib().srcfd_initialize_fields(self._h, C.c_int(int(zero_first))))
+
+    def set_fields(self, fields: np.ndarray):
+        f = np.ascontiguousarray(fields)
+        assert f.shape == (3, self.ny, self.nx), (f.shape, (3, self.ny, self.nx))
+        if f.dtype == np.float32:
+            check(lib().srcfd_set_fields(self._h, f.ctypes.data_as(C.c_void_p), C.c_int(1)))
+        else:
+            f = np.ascontiguousarray(f, dtype=np.float64)
+            check(lib().srcfd_set_fields(self._h, f.ctypes.data_as(C.c_void_p), C.c_int(0)))
+
+    def step(self, n_outer: int, crit=(1e-6, 1e-6, 1e-6)):
+        c = (C.c_double * 3)(*[float(x) for x in crit])
+        check(lib().srcfd_step(self._h, C.c_int64(int(n_outer)), c))
+
+    def status(self):
+        it, conv = C.c_int64(0), C.c_int32(0)
+        rms, ls, ts = (C.c_double * 3)(), (C.c_int32 * 3)(), (C.c_int64 * 3)()
+        check(lib().srcfd_status(self._h, C.byref(it), C.byref(conv), rms, ls, ts))
+        return dict(iterations=it.value, converged=bool(conv.value), rms=np.array(rms[:]),
+                    last_sweeps=np.array(ls[:]), total_sweeps=np.array(ts[:]))
+
+    def reset_counters(self):
+        check(lib().srcfd_reset_counters(self._h))
+
+    def solve(self, max_iterations: int, crit=(1e-6, 1e-6, 1e-6)):
+        c = (C.c_double * 3)(*[float(x) for x in crit])
+        cap = int(max_iterations) // 100 + 1
+        hist = np.zeros((cap, 3))
+        it, nh, sec = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+        check(lib().srcfd_solve(self._h, C.c_int64(int(max_iterations)), c, C.byref(it), C.byref(sec), _ptr(hist),
+                                C.c_int64(cap), C.byref(nh)))
+        return it.value, sec.value, hist[: nh.value]
+
+    # ---- kernel level
+    def k_copy_new_to_old(self):
+        check(lib().srcfd_k_copy_new_to_old(self._h))
+
+    def k_apply_bc(self, k):
+        check(lib().srcfd_k_apply_bc(self._h, C.c_int(int(k))))
+
+    def k_apply_bc_configured(self, k):
+        check(lib().srcfd_k_apply_bc_configured(self._h, C.c_int(int(k))))
+
+    def k_apply_bfs_inlet(self, k):
+        check(lib().srcfd_k_apply_bfs_inlet(self._h, C.c_int(int(k))))
+
+    def k_linear_interpolation(self):
+        check(lib().srcfd_k_linear_interpolation(self._h))
+
+    def k_update_flux(self):
+        check(lib().srcfd_k_update_flux(self._h))
+
+    def k_under_relax(self, k, alpha):
+        check(lib().srcfd_k_under_relax(self._h, C.c_int(int(k)), C.c_double(float(alpha))))
+
+    def k_correct_velocity(self):
+        r = (C.c_double * 3)()
+        check(lib().srcfd_k_correct_velocity(self._h, r))
+        return np.array(r[:])
+
+    def k_solve_pressure(self):
+        n, rms = C.c_int32(0), C.c_double(0.0)
+        check(lib().srcfd_k_solve_pressure(self._h, C.byref(n), C.byref(rms)))
+        return n.value, rms.value
+
+    def k_solve_momentum(self, k, scheme):
+        n, rms = C.c_int32(0), C.c_double(0.0)
+        check(lib().srcfd_k_solve_momentum(self._h, C.c_int(int(k)), C.c_int(int(scheme)), C.byref(n), C.byref(rms)))
+        return n.value, rms.value
+
+    def k_implicit_solve(self):
+        check(lib().srcfd_k_implicit_solve(self._h))
+
+    # ---- introspection
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        check(lib().srcfd_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def timing_enable(self, on=True):
+        check(lib().srcfd_timing_enable(self._h, C.c_int(int(on))))
+
+    def timing_read(self):
+        pm, mm, pn, mn = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+        check(lib().srcfd_timing_read(self._h, C.byref(pm), C.byref(pn), C.byref(mm), C.byref(mn)))
+        return dict(pressure_ms=pm.value, pressure_launches=pn.value, momentum_ms=mm.value, momentum_launches=mn.value)

@@ -1,0 +1,218 @@
+"""Parity of the CUDA path (through the C ABI / ctypes) against the CPU oracle.  `-m gpu`.
+
+Bars: fields BIT-EXACT for every kernel and every sweep order (the kernels evaluate the reference's
+expressions in the reference's order, fp64, no FMA contraction); residual sums to 1e-13 relative
+(fixed-order tree sums on the device vs the reference's sequential sum).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from srcfd import kernels
+    return kernels
+
+
+def rnd_state(seed, Nx, Ny, ff_scale=0.05):
+    rng = np.random.default_rng(seed)
+    Var = rng.uniform(-1, 1, (3, Nx + 2, Ny + 2))
+    VarOld = Var + 0.01 * rng.uniform(-1, 1, Var.shape)
+    Ff = ff_scale * rng.uniform(-1, 1, (4, Nx + 2, Ny + 2))
+    return Var, VarOld, Ff
+
+
+SIZES = [(1, 1), (2, 3), (13, 9), (64, 48), (33, 130)]
+
+
+@pytest.mark.parametrize("Nx,Ny", SIZES)
+def test_tail_kernels_bit_exact(K, Nx, Ny):
+    Var, VarOld, Ff = rnd_state(Nx * 100 + Ny, Nx, Ny)
+    dx, dy, dt, rho = 1.3 / Nx, 0.9 / Ny, 2e-3, 1.0
+    A, B = Ff.copy(), Ff.copy()
+    K.linear_interpolation(Var, A, Nx, Ny, dx, dy); O.linear_interpolation(Var, B, Nx, Ny, dx, dy)
+    assert np.array_equal(A, B)
+    A, B = Ff.copy(), Ff.copy()
+    K.update_flux(Var, A, dt, rho, Nx, Ny, dx, dy); O.update_flux(Var, B, dt, rho, Nx, Ny, dx, dy)
+    assert np.array_equal(A, B)
+    for k in range(3):
+        t = np.array([k % 2, 1, 0, (k + 1) % 2], dtype=np.int32); v = np.array([0.3, -0.2, 1.0, 0.5])
+        A, B = Var.copy(), Var.copy()
+        K.apply_bc_configured(A, k, Nx, Ny, t, v); O.apply_bc_configured(B, k, Nx, Ny, t, v)
+        assert np.array_equal(A, B)
+    for k in (0, 1, 2):
+        A, B = Var.copy(), Var.copy()
+        K.apply_bfs_inlet(A, k, Nx, Ny, 3.0 / Ny, 1.0, 2.0, 1.0); O.apply_bfs_inlet(B, k, Nx, Ny, 3.0 / Ny, 1.0, 2.0, 1.0)
+        assert np.array_equal(A, B)
+    A, B = Var.copy(), Var.copy()
+    K.under_relax_field(A, VarOld, 1, Nx, Ny, 0.5); O.under_relax_field(B, VarOld, 1, Nx, Ny, 0.5)
+    assert np.array_equal(A, B)
+    A, B = VarOld.copy(), VarOld.copy()
+    K.copy_new_to_old(Var, A, 3, Nx, Ny); O.copy_new_to_old(Var, B, 3, Nx, Ny)
+    assert np.array_equal(A, B)
+    A, B = Var.copy(), Var.copy()
+    ra, rb = np.array([0.5, 0.25, 0.125]), np.array([0.5, 0.25, 0.125])
+    K.correct_velocity(A, VarOld, dt, rho, Nx, Ny, dx, dy, ra); O.correct_velocity(B, VarOld, dt, rho, Nx, Ny, dx, dy, rb)
+    assert np.array_equal(A, B)
+    np.testing.assert_allclose(ra, rb, rtol=1e-13)
+
+
+ORDERS = [("GS_LEX", O.ORDER_GS_LEX), ("JACOBI", O.ORDER_JACOBI), ("RED_BLACK", O.ORDER_RB)]
+
+
+@pytest.mark.parametrize("Nx,Ny", SIZES + [(600, 20), (1100, 7)])     # the last two span 2 and 3 row bands
+@pytest.mark.parametrize("oname,ocode", ORDERS)
+def test_inner_solves_bit_exact(K, Nx, Ny, oname, ocode):
+    Var, VarOld, Ff = rnd_state(7 + Nx + Ny, Nx, Ny)
+    dx, dy = 1.3 / Nx, 0.9 / Ny
+    volp, dt, nu, rho = dx * dy, 2e-3, 1 / 250.0, 1.0
+    cap = 60
+    A, B = Var.copy(), Var.copy()
+    n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, dt, rho, volp, sweep_order=oname, max_iter=cap)
+    m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, dt, rho, volp, order=ocode, max_iter=cap)
+    assert n == m and np.array_equal(A, B), (n, m, np.max(np.abs(A - B)))
+    for k in (0, 1):
+        A, B = Var.copy(), Var.copy()
+        n = K.solve_momentum_upwind(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, sweep_order=oname, max_iter=cap)
+        m = O.solve_momentum_upwind(B, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, order=ocode, max_iter=cap)
+        assert n == m and np.array_equal(A, B), ("upwind", k, n, m, np.max(np.abs(A - B)))
+        if oname == "RED_BLACK":
+            continue            # undefined for the 9-point QUICK stencil; the library refuses it
+        A, B = Var.copy(), Var.copy()
+        n = K.solve_momentum_quick(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, sweep_order=oname, max_iter=cap)
+        m = O.solve_momentum_quick(B, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, order=ocode, max_iter=cap)
+        assert n == m and np.array_equal(A, B), ("quick", k, n, m, np.max(np.abs(A - B)))
+
+
+def test_break_semantics_and_rollback(K):
+    """Exact 'stop after the first sweep with rms < tol' behaviour, including the speculative-group
+    rollback of the wavefront order (the cached handle carries the previous call's sweep count as its guess)."""
+    Nx, Ny = 40, 30
+    Var, VarOld, Ff = rnd_state(99, Nx, Ny, ff_scale=0.01)
+    dx, dy = 1.0 / Nx, 1.0 / Ny
+    volp, dt, nu = dx * dy, 1e-3, 0.01
+    counts = []
+    for tol in (1e-3, 1e-9, 1e-5, 1e-12, 1e-4, 1e-7):          # guesses alternately too large / too small
+        A, B = Var.copy(), Var.copy()
+        n = K.solve_momentum_upwind(A, VarOld, Ff, 0, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=400)
+        m = O.solve_momentum_upwind(B, VarOld, Ff, 0, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=400)
+        assert n == m and np.array_equal(A, B), (tol, n, m)
+        counts.append(n)
+    assert len(set(counts)) > 3
+
+
+def test_golden_numba_kernels(K, golden_dir):
+    """CUDA path against outputs of the reference's own numba kernels (tests/golden/numba_kernels.npz)."""
+    g = np.load(os.path.join(golden_dir, "numba_kernels.npz"))
+    Nx, Ny = int(g["Nx"]), int(g["Ny"])
+    dx, dy, volp, dt, nu, rho = (float(g[k]) for k in ("dx", "dy", "volp", "dt", "nu", "rho"))
+    Var, VarOld, Ff = g["Var"], g["VarOld"], g["Ff"]
+    A = Ff.copy(); K.linear_interpolation(Var, A, Nx, Ny, dx, dy); assert np.array_equal(A, g["linear_interpolation"])
+    A = Ff.copy(); K.update_flux(Var, A, dt, rho, Nx, Ny, dx, dy); assert np.array_equal(A, g["update_flux"])
+    A = Var.copy(); K.solve_pressure(A, Ff, Nx, Ny, dx, dy, dt, rho, volp); assert np.array_equal(A, g["solve_pressure"])
+    for k in (0, 1):
+        A = Var.copy(); K.solve_momentum_upwind(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp)
+        assert np.array_equal(A, g[f"solve_momentum_upwind_k{k}"])
+        A = Var.copy(); K.solve_momentum_quick(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp)
+        assert np.array_equal(A, g[f"solve_momentum_quick_k{k}"])
+    A = Var.copy(); r = np.zeros(3); K.correct_velocity(A, VarOld, dt, rho, Nx, Ny, dx, dy, r)
+    assert np.array_equal(A, g["correct_velocity"])
+    np.testing.assert_allclose(r, g["correct_velocity_residual"], rtol=1e-13)
+
+
+def _bfs_bc(mod):
+    bc = mod.BoundaryConditions()
+    bc.u_boundaries['left'] = mod.BoundaryCondition('dirichlet', 0.0)
+    bc.u_boundaries['right'] = mod.BoundaryCondition('neumann', 0.0)
+    bc.v_boundaries['right'] = mod.BoundaryCondition('neumann', 0.0)
+    bc.p_boundaries['right'] = mod.BoundaryCondition('dirichlet', 0.0)
+    return bc
+
+
+def test_golden_numba_solves(golden_dir):
+    """Drop-in CFDSolver against the reference's own CFDSolver.solve() outputs (numba_solves.npz)."""
+    from srcfd import bfs, ldc
+    g = np.load(os.path.join(golden_dir, "numba_solves.npz"))
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=24, ny=20), ldc.FluidProperties(Re=100.0),
+                      ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=30), ldc.BoundaryConditions())
+    n, _ = s.solve("x", verbose=False, save=False)
+    assert n == 30 and np.array_equal(s.Var, g["ldc_24x20_quick_30_Var"])
+    assert np.array_equal(s.VarOld, g["ldc_24x20_quick_30_VarOld"]) and np.array_equal(s.Ff, g["ldc_24x20_quick_30_Ff"])
+    s = bfs.CFDSolver(bfs.MeshParameters(nx=20, ny=16), bfs.FluidProperties(Re=400.0),
+                      bfs.SolverSettings(dt=2e-3, scheme='UPWIND', max_iterations=250), _bfs_bc(bfs))
+    s.solve("x", verbose=False, save=False)
+    assert np.array_equal(s.Var, g["bfs_20x16_upwind_250_Var"]) and np.array_equal(s.Ff, g["bfs_20x16_upwind_250_Ff"])
+    hist = np.array([s.residual_history[k] for k in "uvp"]).T
+    np.testing.assert_allclose(hist, g["bfs_20x16_upwind_250_hist"], rtol=1e-12)
+    s = bfs.CFDSolver(bfs.MeshParameters(nx=20, ny=16), bfs.FluidProperties(Re=400.0),
+                      bfs.SolverSettings(dt=2e-3, scheme='QUICK', max_iterations=40), _bfs_bc(bfs))
+    s.solve("x", verbose=False, save=False)
+    assert np.array_equal(s.Var, g["bfs_20x16_quick_40_Var"])          # QUICK out-of-plane reads (H4) on the inlet
+
+
+def test_warm_start_golden(golden_dir):
+    from srcfd import ldc
+    g = np.load(os.path.join(golden_dir, "numba_solves.npz"))
+    w = g["warm_fields"]
+    ldc._wf.verbose = False
+    s, n, _ = ldc.run_fine_simulation_with_ml_init(100.0, 24, 20, {"u": w[0], "v": w[1], "p": w[2]}, dt=1e-3,
+                                                   scheme='QUICK', max_iterations=5, save=False)
+    assert n == 5 and np.array_equal(s.Var, g["warm_ldc_24x20_quick_5_Var"])
+
+
+@pytest.mark.parametrize("order,ocode", ORDERS[:2])
+def test_composed_solver_vs_oracle(order, ocode):
+    """Whole outer iterations (momentum x2, interpolation, pressure, correction, BCs, flux update,
+    convergence bookkeeping) at a size with real pipelining."""
+    from srcfd import ldc
+    nx, ny, its = 96, 72, 12
+    st = ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=its, sweep_order=order)
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=nx, ny=ny), ldc.FluidProperties(Re=100.0), st, ldc.BoundaryConditions())
+    n, _ = s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme="QUICK", order=ocode))
+    m, rms, _ = o.solve(its)
+    assert n == m == its
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.VarOld, o.VarOld) and np.array_equal(s.Ff, o.Ff)
+    assert s.total_sweeps.tolist() == o.total_sweeps.tolist()
+    np.testing.assert_allclose(np.sqrt(s.residual / (nx * ny)) / 1e-3, rms, rtol=1e-12)
+
+
+def test_stepwise_api_matches_solve():
+    """_implicit_solve / _convergence_check (host-array API) == solve()."""
+    from srcfd import bfs
+    mk = lambda: bfs.CFDSolver(bfs.MeshParameters(nx=30, ny=24), bfs.FluidProperties(Re=400.0),
+                               bfs.SolverSettings(dt=2e-3, max_iterations=4), _bfs_bc(bfs))
+    a, b = mk(), mk()
+    a.solve("x", verbose=False, save=False)
+    for _ in range(4):
+        b._implicit_solve()
+        conv, rms = b._convergence_check()
+    assert np.array_equal(a.Var, b.Var) and np.array_equal(a.VarOld, b.VarOld) and np.array_equal(a.Ff, b.Ff)
+
+
+def test_nan_raises_value_error():
+    from srcfd import ldc
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=16, ny=16), ldc.FluidProperties(Re=100.0),
+                      ldc.SolverSettings(dt=1e-3, max_iterations=3), ldc.BoundaryConditions())
+    s.Var[0, 5, 5] = np.nan
+    with pytest.raises(ValueError, match="NaN/Inf in residuals"):
+        s.solve("x", verbose=False, save=False)
+
+
+def test_bfs_sir_late_case_type():
+    """"bfs code given by sir.py":856-861 sets case_type after construction: first BC pass has no inlet."""
+    from srcfd import ldc, solver as S
+    bc = _bfs_bc(ldc)
+    bc.u_boundaries['top'] = ldc.BoundaryCondition('dirichlet', 0.0)
+    st = S.BFSSolverSettings(dt=2e-3, scheme='UPWIND', max_iterations=300, relaxation_factors={'u': .5, 'v': .5, 'p': .2})
+    s = S.CFDSolver(S.MeshParameters(nx=10, ny=10, lx=10.0, ly=3.0), S.FluidProperties(Re=400), st, bc, relaxed=True)
+    s.case_type, s.h, s.step_height, s.Ub = 'BFS', 2.0, 1, 1.0
+    s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.bfs_case(10, 10), bfs_at_init=False); o.solve(300)
+    assert np.array_equal(s.Var, o.Var)
