@@ -113,6 +113,10 @@ int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, 
 int srcfd_k_implicit_solve(srcfd_handle *h);
 
 /* ---- introspection for benchmarks ---------------------------------------------------------- */
+/* CUDA-event stopwatch on the handle's stream: start records an event, stop records a second one,
+ * waits for it and returns the device time between them in milliseconds. */
+int srcfd_timer_start(srcfd_handle *h);
+int srcfd_timer_stop(srcfd_handle *h, double *ms);
 /* Number of kernels this library has launched on the handle's stream since creation. */
 int srcfd_launch_count(srcfd_handle *h, int64_t *launches);
 /* Device time (ms) and launches of the inner-solve kernels accumulated while timing is enabled

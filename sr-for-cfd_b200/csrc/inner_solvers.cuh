@@ -146,9 +146,9 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_solve_sync(SolveArgs a) {
 //   * tasks are dealt round-robin to the persistent CTAs in (s,b) order, and every dependence points
 //     to an earlier task, so the grid is a feed-forward pipeline: sweep s+1 trails sweep s by a few
 //     columns, synchronised by per-task progress counters in global memory (release/acquire);
-//   * each thread reads its own row WF_D columns ahead into registers (L1-bypassing loads: the data is
+//   * each thread reads its own row a few columns ahead into a register ring (L1-bypassing loads: the data is
 //     produced by other SMs during the kernel).
-// With W = WF_D + 5, before step tau of task (s,b) starts the following must have been published
+// With W = R + 1 (R = ring size, see WfShape), before step tau of task (s,b) starts the following must have been published
 // (P = completed steps of a task, capped at that task's step count):
 //     P(s-1, b)   >= tau + W                     own rows hold sweep s-1
 //     P(s-1, b+1) >= tau + W - nrows(b)          rows below hold sweep s-1
@@ -161,44 +161,119 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_solve_sync(SolveArgs a) {
 // that many sweeps.  The group size is the previous outer iteration's count, so the common case is
 // one pass.
 // ---------------------------------------------------------------------------------------------------
-constexpr int WF_D = 4;             // row look-ahead (steps) kept in registers
-constexpr int WF_W = WF_D + 5;      // dependence look-ahead, see above
-constexpr int WF_C = 4;             // publish progress every WF_C steps
-constexpr int WF_MAX_THREADS = 512; // band rows + 4 passive threads, rounded to a warp multiple
-constexpr int WF_MAX_BAND = WF_MAX_THREADS - 4;
+constexpr int WF_SVC = 64;           // two service warps: publisher (first lane of warp -2) and poller (warp -1)
+constexpr int WF_MAX_THREADS = 512;  // band rows + 4 passive threads (warp-rounded) + service warps
+constexpr int WF_MAX_BAND = WF_MAX_THREADS - WF_SVC - 4;
+
+// Per-operator pipeline shape.  WIN = columns jj..jj+WIN-1 a thread must hold (itself + what it
+// publishes to the rows above); D = extra columns in flight from L2; R = WIN + D is both the register
+// ring size and the unroll factor of the step loop (ring slots are addressed by step parity, so no
+// register is ever moved while its load is outstanding).  AR = ring for the read-only inputs.
+template <int OP> struct WfShape;
+template <> struct WfShape<OP_PRESSURE> { static constexpr int WIN = 3, D = 3, R = 6, AR = 3; };
+template <> struct WfShape<OP_UPWIND>   { static constexpr int WIN = 3, D = 3, R = 6, AR = 3; };
+template <> struct WfShape<OP_QUICK>    { static constexpr int WIN = 4, D = 4, R = 8, AR = 4; };
 
 template <int OP> struct WfAux;
 template <> struct WfAux<OP_PRESSURE> { double rhs; };
 template <> struct WfAux<OP_UPWIND> { double vold, fE, fN, fW, fS; };
 template <> struct WfAux<OP_QUICK> { double vold, fE, fN, fW, fS; };
 
-__device__ __forceinline__ void wf_wait(const int* flag, int need, int& cache, const SolveArgs& a) {
-    if (cache >= need) return;
-    int spins = 0;
-    while ((cache = ld_acquire(flag)) < need) {
-        if (++spins > a.spin_limit || ld_volatile(&a.ctrl->deadlock)) {
-            a.ctrl->deadlock = 1;     // guard: never hang the GPU; the host reports SRCFD_ERR_DEADLOCK
-            cache = 0x7fffffff;
-            break;
-        }
-        __nanosleep(64);
-    }
+__device__ __forceinline__ int lds_volatile(const int* p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(int* p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bar_compute(int nthreads) {   // named barrier 1: compute warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+constexpr int WF_INF = 0x3fffffff;
+
+// One task = (sweep s, band b).  Threads [0, NT-WF_SVC) compute; the two service warps run beside them,
+// off the per-step critical path:
+//   publisher  watches s_sync[0] (= number of completed steps, written by a compute thread right after
+//              the step barrier), then fence + release-store of that number to the task's global flag;
+//   poller     reads the three dependence flags and keeps s_sync[1] = highest step index that may start.
 template <int OP>
-__device__ void wf_task(const SolveArgs& a, const int s, const int b, double* smem, double& acc_out) {
+__device__ void wf_task(const SolveArgs& a, const int s, const int b, double* smem, int* s_sync, double& acc_out) {
     const Consts& K = a.K;
     constexpr bool Q = (OP == OP_QUICK);
+    constexpr int R = WfShape<OP>::R, AR = WfShape<OP>::AR;
+    constexpr int W = R + 1;               // dependence look-ahead in steps (see the block comment above)
     const int NT = blockDim.x, tid = threadIdx.x, SP = NT + 4;
-    double* s_new = smem + 2;              // [2][SP], index = buf*SP + tid, valid tid range -2 .. NT+1
-    double* s_c   = smem + 2 + 2 * SP;
-    double* s_im  = smem + 2 + 4 * SP;
-    double* s_c2  = smem + 2 + 6 * SP;
+    const int NCOMP = NT - WF_SVC;
+    // volatile: the per-step barrier is inline PTX (named barrier 1); keep the compiler from caching these across it
+    volatile double* s_new = smem + 2;     // [2][SP], index = buf*SP + tid, valid tid range -2 .. NT+1
+    volatile double* s_c   = smem + 2 + 2 * SP;
+    volatile double* s_im  = smem + 2 + 4 * SP;
+    volatile double* s_c2  = smem + 2 + 6 * SP;
 
     const int B = a.nbands;
     const int i0 = 1 + b * a.band_rows;
     const int nrows = min(a.band_rows, K.nx - i0 + 1);
     const int nsteps = K.ny + nrows - 1;
+
+    const int* f_prev  = (s > 0) ? a.prog + (size_t)(s - 1) * B + b : nullptr;
+    const int* f_below = (s > 0 && b + 1 < B) ? a.prog + (size_t)(s - 1) * B + b + 1 : nullptr;
+    const int* f_above = (b > 0) ? a.prog + (size_t)s * B + b - 1 : nullptr;
+    int* my_flag = a.prog + (size_t)s * B + b;
+
+    if (tid == 0) {
+        sts_volatile(&s_sync[0], 0);
+        sts_volatile(&s_sync[1], (f_prev || f_below || f_above) ? -WF_INF : WF_INF);
+    }
+    __syncthreads();
+    acc_out = 0.0;
+
+    if (tid >= NCOMP) {
+        if (tid == NT - WF_SVC) {                       // ---- publisher
+            int last = 0;
+            while (last < nsteps) {
+                const int d = lds_volatile(&s_sync[0]);
+                if (d > last) { __threadfence(); st_release(my_flag, d); last = d; }
+                else __nanosleep(20);
+            }
+        } else if (tid == NT - 32 && (f_prev || f_below || f_above)) {   // ---- poller
+            const int nrows_below = (b + 1 < B) ? min(a.band_rows, K.nx - (i0 + a.band_rows) + 1) : 0;
+            const int nsteps_below = K.ny + nrows_below - 1;
+            const int nsteps_above = K.ny + a.band_rows - 1;
+            int c1 = 0, c2 = 0, c3 = 0, cur = -WF_INF, spins = 0;
+            while (true) {
+                if (f_prev && c1 < nsteps) c1 = ld_relaxed(f_prev);
+                if (f_below && c2 < nsteps_below) c2 = ld_relaxed(f_below);
+                if (f_above && c3 < nsteps_above) c3 = ld_relaxed(f_above);
+                const int a1 = (!f_prev || c1 >= nsteps) ? WF_INF : c1 - W;
+                const int a2 = (!f_below || c2 >= nsteps_below) ? WF_INF : c2 - W + nrows;
+                const int a3 = (!f_above || c3 >= nsteps_above) ? WF_INF : c3 - W - a.band_rows;
+                const int al = min(a1, min(a2, a3));
+                if (al > cur) {
+                    __threadfence();                      // acquire side of the producers' release stores
+                    sts_volatile(&s_sync[1], al);
+                    cur = al; spins = 0;
+                }
+                if (al >= nsteps) break;
+                if (++spins > a.spin_limit || ld_volatile(&a.ctrl->deadlock)) {
+                    a.ctrl->deadlock = 1;                 // guard: never hang the GPU (host reports SRCFD_ERR_DEADLOCK)
+                    sts_volatile(&s_sync[1], WF_INF);
+                    break;
+                }
+                __nanosleep(20);
+            }
+        }
+        __syncthreads();
+        return;
+    }
+
+    // ------------------------------------------ compute threads --------------------------------
     const int r = tid - 2;
     const int irow = i0 + r;
     const bool regular = (r >= 0 && r < nrows);
@@ -207,23 +282,23 @@ __device__ void wf_task(const SolveArgs& a, const int s, const int b, double* sm
 
     // row bases; irow = -1 wraps to nx+1, irow = nx+2 runs on into the next plane (hazard H4)
     const long long rowoff = (irow < 0) ? (long long)(K.nx + 2 + irow) * K.pitch : (long long)irow * K.pitch;
-    const double* rowp = a.Var + (long long)a.k * K.plane + rowoff;
+    const double* rowp = a.Var + (long long)a.k * K.plane + (live ? rowoff : 0);
     double* wrow = a.Var + (long long)a.k * K.plane + rowoff;
     const double* aux0 = (OP == OP_PRESSURE) ? a.rhs + rowoff : a.VarOld + (long long)a.k * K.plane + rowoff;
     const double* auxF = a.Ff + rowoff;
+    const int colmax = K.ny + 2;
 
     auto ldc = [&](int col) -> double {
-        if (!live) return 0.0;
         if (col == -1) col = K.ny + 1;
-        if (col < 0 || col > K.ny + 2) return 0.0;
-        return __ldcg(rowp + col);
+        return (live && col >= 0 && col <= colmax) ? __ldcg(rowp + col) : 0.0;
     };
     auto lda = [&](int col) -> WfAux<OP> {
         WfAux<OP> x;
+        const bool ok = regular && col >= 1 && col <= K.ny;
         if constexpr (OP == OP_PRESSURE) {
-            x.rhs = (regular && col >= 1 && col <= K.ny) ? __ldg(aux0 + col) : 0.0;
+            x.rhs = ok ? __ldg(aux0 + col) : 0.0;
         } else {
-            if (regular && col >= 1 && col <= K.ny) {
+            if (ok) {
                 x.vold = __ldg(aux0 + col);
                 x.fE = __ldg(auxF + col); x.fN = __ldg(auxF + K.plane + col);
                 x.fW = __ldg(auxF + 2 * K.plane + col); x.fS = __ldg(auxF + 3 * K.plane + col);
@@ -231,95 +306,81 @@ __device__ void wf_task(const SolveArgs& a, const int s, const int b, double* sm
         }
         return x;
     };
-
-    // ---- dependence bookkeeping (one polling thread) -------------------------------------------
-    const int poller = NT - 1;
-    const int* f_prev  = (s > 0) ? a.prog + (size_t)(s - 1) * B + b : nullptr;
-    const int* f_below = (s > 0 && b + 1 < B) ? a.prog + (size_t)(s - 1) * B + b + 1 : nullptr;
-    const int* f_above = (b > 0) ? a.prog + (size_t)s * B + b - 1 : nullptr;
-    const int nrows_below = (b + 1 < B) ? min(a.band_rows, K.nx - (i0 + a.band_rows) + 1) : 0;
-    const int nsteps_below = K.ny + nrows_below - 1;
-    const int nsteps_above = K.ny + a.band_rows - 1;
-    int c_prev = 0, c_below = 0, c_above = 0;
-    auto ensure = [&](int tau) {
-        if (f_prev) wf_wait(f_prev, min(nsteps, tau + WF_W), c_prev, a);
-        if (f_below) { const int need = min(nsteps_below, tau + WF_W - nrows); if (need > 0) wf_wait(f_below, need, c_below, a); }
-        if (f_above) wf_wait(f_above, min(nsteps_above, tau + WF_W + a.band_rows), c_above, a);
+    int allowed = -WF_INF;
+    auto wait_allowed = [&](int tau) {
+        while (allowed < tau) allowed = lds_volatile(&s_sync[1]);
     };
-    int* my_flag = a.prog + (size_t)s * B + b;
 
-    if (tid == poller) ensure(-2);
-    __syncthreads();
-
-    // ---- window set-up at tau = -2 ---------------------------------------------------------------
+    // ---- window set-up at tau = -2: ring[m] = C[jj+m] ---------------------------------------------
+    wait_allowed(-2);
     int jj = -2 - r + 1;
-    double w0 = ldc(jj), w1 = ldc(jj + 1), w2 = ldc(jj + 2), w3 = ldc(jj + 3);
-    double q[WF_D];
+    double ring[R];
 #pragma unroll
-    for (int d = 0; d < WF_D; ++d) q[d] = ldc(jj + 4 + d);
-    WfAux<OP> ax[WF_D];
+    for (int m = 0; m < R; ++m) ring[m] = ldc(jj + m);
+    WfAux<OP> ax[AR];
 #pragma unroll
-    for (int d = 0; d < WF_D; ++d) ax[d] = lda(jj + d);
-    double prev1 = regular ? ldc(0) : 0.0;      // (i, 0)   ghost column
+    for (int m = 0; m < AR; ++m) ax[m] = lda(jj + m);
+    double prev1 = regular ? ldc(0) : 0.0;          // (i, 0)   ghost column
     double prev2 = (regular && Q) ? ldc(-1) : 0.0;  // (i, -1) -> (i, ny+1) by index wrap
     double acc = 0.0;
 
-    for (int tau = -2; tau < nsteps; ++tau) {
-        __syncthreads();
-        const int pb = tau & 1, cb = pb ^ 1;     // buffers: read what step tau-1 published
-        if (tid == 0 && tau > 0 && (tau % WF_C) == 0) { __threadfence(); st_release(my_flag, tau); }
-        const double qn = ldc(jj + 4 + WF_D);
-        const WfAux<OP> an = lda(jj + WF_D);
-
-        const double im = s_new[pb * SP + tid - 1];
-        const double ip = s_c[pb * SP + tid + 1];
-        double im2 = 0.0, ip2 = 0.0;
-        if (Q) { im2 = s_im[pb * SP + tid - 1]; ip2 = s_c2[pb * SP + tid + 2]; }
-
-        double outv = w0;
-        if (regular && jj >= 1 && jj <= K.ny) {
-            double R, nv;
-            if constexpr (OP == OP_PRESSURE) nv = pressure_cell(w0, ip, im, w1, prev1, ax[0].rhs, K, R);
-            else if constexpr (OP == OP_UPWIND)
-                nv = upwind_cell(w0, ip, im, w1, prev1, ax[0].vold, ax[0].fE, ax[0].fN, ax[0].fW, ax[0].fS, K, R);
-            else
-                nv = quick_cell(w0, ip, im, w1, prev1, ip2, im2, w2, prev2, ax[0].vold, ax[0].fE, ax[0].fN, ax[0].fW, ax[0].fS, K, R);
-            wrow[jj] = nv;
-            acc += R * R;
-            outv = nv;
-            prev2 = prev1; prev1 = nv;
-        }
-        s_new[cb * SP + tid] = outv;
-        s_c[cb * SP + tid] = w2;
-        if (Q) { s_im[cb * SP + tid] = im; s_c2[cb * SP + tid] = w3; }
-
-        w0 = w1; w1 = w2; w2 = w3; w3 = q[0];
+    for (int tau0 = -2; tau0 < nsteps; tau0 += R) {
 #pragma unroll
-        for (int d = 0; d + 1 < WF_D; ++d) { q[d] = q[d + 1]; ax[d] = ax[d + 1]; }
-        q[WF_D - 1] = qn; ax[WF_D - 1] = an;
-        ++jj;
-        if (tid == poller) ensure(tau + 1);
+        for (int u = 0; u < R; ++u) {
+            const int tau = tau0 + u;
+            if (tau >= nsteps) break;
+            bar_compute(NCOMP);
+            const int pb = tau & 1, cb = pb ^ 1;     // read what step tau-1 published
+            if (tid == 0 && tau > 0) sts_volatile(&s_sync[0], tau);   // steps < tau are complete
+            wait_allowed(tau);
+
+            const double w0 = ring[u % R], w1 = ring[(u + 1) % R], w2 = ring[(u + 2) % R];
+            const double w3 = Q ? ring[(u + 3) % R] : 0.0;
+            const WfAux<OP> x = ax[u % AR];
+            const double im = s_new[pb * SP + tid - 1];
+            const double ip = s_c[pb * SP + tid + 1];
+            double im2 = 0.0, ip2 = 0.0;
+            if (Q) { im2 = s_im[pb * SP + tid - 1]; ip2 = s_c2[pb * SP + tid + 2]; }
+
+            double outv = w0;
+            if (regular && jj >= 1 && jj <= K.ny) {
+                double Rr, nv;
+                if constexpr (OP == OP_PRESSURE) nv = pressure_cell(w0, ip, im, w1, prev1, x.rhs, K, Rr);
+                else if constexpr (OP == OP_UPWIND)
+                    nv = upwind_cell(w0, ip, im, w1, prev1, x.vold, x.fE, x.fN, x.fW, x.fS, K, Rr);
+                else
+                    nv = quick_cell(w0, ip, im, w1, prev1, ip2, im2, w2, prev2, x.vold, x.fE, x.fN, x.fW, x.fS, K, Rr);
+                wrow[jj] = nv;
+                acc += Rr * Rr;
+                outv = nv;
+                prev2 = prev1; prev1 = nv;
+            }
+            s_new[cb * SP + tid] = outv;
+            s_c[cb * SP + tid] = w2;
+            if (Q) { s_im[cb * SP + tid] = im; s_c2[cb * SP + tid] = w3; }
+
+            // refill the slots just consumed: column jj+R of the row, column jj+AR of the inputs
+            ring[u % R] = ldc(jj + R);
+            ax[u % AR] = lda(jj + AR);
+            ++jj;
+        }
     }
-    __syncthreads();
+    bar_compute(NCOMP);
+    if (tid == 0) sts_volatile(&s_sync[0], nsteps);
     acc_out = acc;
+    __syncthreads();
 }
 
 template <int OP>
-__device__ void wf_run(const SolveArgs& a, int n_sweeps, double* smem) {
+__device__ void wf_run(const SolveArgs& a, int n_sweeps, double* smem, int* s_sync) {
     const int B = a.nbands;
     const int ntasks = n_sweeps * B;
     double* red = smem + 8 * (blockDim.x + 4) + 4;
     for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
-        const int s = t / B, b = t % B;
         double acc;
-        wf_task<OP>(a, s, b, smem, acc);
+        wf_task<OP>(a, t / B, t % B, smem, s_sync, acc);
         const double tot = block_sum(acc, red);
-        if (threadIdx.x == 0) {
-            a.partials[t] = tot;
-            const int nrows = min(a.band_rows, a.K.nx - (1 + b * a.band_rows) + 1);
-            __threadfence();
-            st_release(a.prog + t, a.K.ny + nrows - 1);
-        }
+        if (threadIdx.x == 0) a.partials[t] = tot;
         __syncthreads();
     }
 }
@@ -337,6 +398,7 @@ __global__ void __launch_bounds__(WF_MAX_THREADS, 1) k_solve_gs(SolveArgs a) {
     if (a.ctrl->stop) return;
     extern __shared__ double smem[];
     __shared__ int s_first;
+    __shared__ int s_sync[2];
     const Consts& K = a.K;
     double* A = a.Var + (long long)a.k * K.plane;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,7 +416,7 @@ __global__ void __launch_bounds__(WF_MAX_THREADS, 1) k_solve_gs(SolveArgs a) {
         for (long long t = gtid; t < (long long)n_run * a.nbands; t += gsize) a.prog[t] = 0;
         if (threadIdx.x == 0) s_first = 0x7fffffff;
         grid.sync();
-        wf_run<OP>(a, n_run, smem);
+        wf_run<OP>(a, n_run, smem, s_sync);
         grid.sync();
         for (int s = threadIdx.x; s < n_run; s += blockDim.x)
             if (wf_sweep_rms(a, s) < a.tol) atomicMin(&s_first, s);
@@ -376,7 +438,7 @@ __global__ void __launch_bounds__(WF_MAX_THREADS, 1) k_solve_gs(SolveArgs a) {
         for (long long t = gtid; t < K.plane; t += gsize) A[t] = __ldcg(a.scratch + t);
         for (long long t = gtid; t < (long long)(first + 1) * a.nbands; t += gsize) a.prog[t] = 0;
         grid.sync();
-        wf_run<OP>(a, first + 1, smem);
+        wf_run<OP>(a, first + 1, smem, s_sync);
         n_done += first + 1;
         break;
     }

@@ -13,6 +13,7 @@
 #include "cell_ops.cuh"
 #include "tail_kernels.cuh"
 #include "inner_solvers.cuh"
+#include "inner_gs2.cuh"
 
 using namespace srcfd;
 
@@ -58,6 +59,11 @@ struct srcfd_handle {
     double t_ms[2] = {0, 0};
     int64_t t_n[2] = {0, 0};
     int spin_limit = 4000000;
+    int gs_impl = 2;            // 2: K-sweep lock-step wavefront (inner_gs2.cuh), 1: one sweep per CTA
+    Gs2Plan plan2[3];
+    int grid_gs2[3] = {0, 0, 0};
+    double* halo = nullptr;
+    cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
     int inner_cap = 0;          // capacity of the per-sweep buffers (inner_max at creation)
     int guess_bias = 0;
 };
@@ -115,12 +121,56 @@ static const void* pick_gs(int op) {
     return gs_kernel<OP_QUICK>();
 }
 
+template <int OP> static const void* gs2_kernel() { return (const void*)k_solve_gs2<OP>; }
+static const void* pick_gs2(int op) {
+    if (op == OP_PRESSURE) return gs2_kernel<OP_PRESSURE>();
+    if (op == OP_UPWIND) return gs2_kernel<OP_UPWIND>();
+    return gs2_kernel<OP_QUICK>();
+}
+template <int OP> static void shape2(int& K, int& NB, int& MAXT) { K = Wf2Shape<OP>::K; NB = Wf2Shape<OP>::NB; MAXT = Wf2Shape<OP>::MAXT; }
+
+// Row bands for the K-sweep wavefront: (K+1) thread groups of RS slots each (+ service warps) must fit the
+// CTA, and every band needs >= NB*K rows so that the redundant rows of the band above stay inside it.
+static int plan_gs2(srcfd_handle* h, int op) {
+    int K, NB, MAXT;
+    if (op == OP_PRESSURE) shape2<OP_PRESSURE>(K, NB, MAXT);
+    else if (op == OP_UPWIND) shape2<OP_UPWIND>(K, NB, MAXT);
+    else shape2<OP_QUICK>(K, NB, MAXT);
+    const int nx = h->p.nx;
+    const int rs_max = ((MAXT - WF_SVC) / (K + 1)) / 32 * 32;          // slots per group, warp multiple
+    const int rows_max = rs_max - NB * K - 2;                           // band rows that fit
+    Gs2Plan& P = h->plan2[op];
+    P.K = K;
+    int nb = (nx + rows_max - 1) / rows_max;
+    // prefer more, shorter bands while that still fills the GPU no further than its SM count allows
+    for (;; ++nb) {
+        const int br = (nx + nb - 1) / nb;
+        const int nbe = (nx + br - 1) / br;
+        const int last = nx - (nbe - 1) * br;
+        if (br <= rows_max && (nbe == 1 || last >= NB * K)) { P.band_rows = br; P.nbands = nbe; break; }
+        if (nb > nx) return fail(SRCFD_ERR_ARG, "cannot band the grid for the wavefront kernel");
+    }
+    P.RS = ((P.band_rows + NB * K + 2 + 31) / 32) * 32;
+    P.ncomp = (K + 1) * P.RS;
+    P.nthreads = P.ncomp + WF_SVC;
+    P.smem = sizeof(double) * (size_t)(WF2_RING + 1) * P.ncomp;
+    if (P.nthreads > MAXT) return fail(SRCFD_ERR_ARG, "wavefront plan exceeds the CTA size");
+    int occ = 0;
+    CK(cudaFuncSetAttribute(pick_gs2(op), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_gs2(op), P.nthreads, P.smem));
+    if (occ < 1) return fail(SRCFD_ERR_CUDA, "K-sweep wavefront kernel does not fit on an SM");
+    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+    h->grid_gs2[op] = std::max(1, std::min(cap, occ * h->num_sms));
+    return SRCFD_OK;
+}
+
 static int plan_launches(srcfd_handle* h) {
+    for (int op = 0; op < 3; ++op) if (int rc = plan_gs2(h, op)) return rc;
     const int nx = h->p.nx;
     h->nbands = (nx + WF_MAX_BAND - 1) / WF_MAX_BAND;
     h->band_rows = (nx + h->nbands - 1) / h->nbands;
     h->nbands = (nx + h->band_rows - 1) / h->band_rows;
-    h->wf_threads = ((h->band_rows + 4 + 31) / 32) * 32;
+    h->wf_threads = ((h->band_rows + 4 + 31) / 32) * 32 + WF_SVC;
     h->wf_smem = sizeof(double) * (8 * (size_t)(h->wf_threads + 4) + 4 + 32);
     const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
     for (int op = 0; op < 3; ++op) {
@@ -155,11 +205,13 @@ int srcfd_destroy(srcfd_handle* h) {
     if (!h) return SRCFD_OK;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->tm_a) cudaEventDestroy(h->tm_a);
+    if (h->tm_b) cudaEventDestroy(h->tm_b);
     for (auto& e : h->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
-    cudaFree(h->staging);
+    cudaFree(h->staging); cudaFree(h->halo);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -188,6 +240,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if (const char* s = getenv("SRCFD_SPIN_LIMIT")) h->spin_limit = atoi(s);
     if (const char* s = getenv("SRCFD_GUESS_BIAS")) h->guess_bias = atoi(s);
+    if (const char* s = getenv("SRCFD_GS_IMPL")) h->gs_impl = atoi(s);
     if (int rc = plan_launches(h)) return bail(rc);
     const size_t P = (size_t)h->K.plane;
     const size_t pad = 4 * (size_t)h->K.pitch + 64;   // QUICK's flat over-reads stay inside the allocation
@@ -195,11 +248,15 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->VarOld, sizeof(double) * (3 * P + pad)));
     CKB(cudaMalloc(&h->Ff, sizeof(double) * (4 * P + pad)));
     CKB(cudaMalloc(&h->rhs, sizeof(double) * (P + pad)));
-    CKB(cudaMalloc(&h->scratch, sizeof(double) * (P + pad)));
+    CKB(cudaMalloc(&h->scratch, sizeof(double) * (P + pad + 8192)));
     int gmax = std::max(h->grid_sync, std::max(h->grid_gs[0], std::max(h->grid_gs[1], h->grid_gs[2])));
-    h->n_partials = std::max((size_t)h->inner_cap * h->nbands, (size_t)2 * gmax) + 64;
+    int maxbands = h->nbands;
+    for (int op = 0; op < 3; ++op) { maxbands = std::max(maxbands, h->plan2[op].nbands); gmax = std::max(gmax, h->grid_gs2[op]); }
+    h->n_partials = std::max((size_t)h->inner_cap * maxbands, (size_t)2 * gmax) + 64;
+    CKB(cudaMalloc(&h->halo, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64));
+    CKB(cudaMemsetAsync(h->halo, 0, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64, h->stream));
     CKB(cudaMalloc(&h->partials, sizeof(double) * h->n_partials));
-    CKB(cudaMalloc(&h->prog, sizeof(int) * ((size_t)h->inner_cap * h->nbands + 64)));
+    CKB(cudaMalloc(&h->prog, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     CKB(cudaMalloc(&h->res_partials, sizeof(double) * 3 * (size_t)(h->tail_blocks + 1)));
     CKB(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
     CKB(cudaMallocHost(&h->ctrl_host, sizeof(Ctrl)));
@@ -208,7 +265,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMemsetAsync(h->Ff, 0, sizeof(double) * (4 * P + pad), h->stream));
     CKB(cudaMemsetAsync(h->rhs, 0, sizeof(double) * (P + pad), h->stream));
     CKB(cudaMemsetAsync(h->scratch, 0, sizeof(double) * (P + pad), h->stream));
-    CKB(cudaMemsetAsync(h->prog, 0, sizeof(int) * ((size_t)h->inner_cap * h->nbands + 64), h->stream));
+    CKB(cudaMemsetAsync(h->prog, 0, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64), h->stream));
     memset(h->ctrl_host, 0, sizeof(Ctrl));
     h->ctrl_host->guess[0] = h->ctrl_host->guess[1] = std::min(8, h->p.inner_max);
     h->ctrl_host->guess[2] = h->p.inner_max;
@@ -362,7 +419,14 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
     void* args[] = {&a};
     EvPair ev;
     if (h->timing) if (int rc = ev_begin(h, op == OP_PRESSURE ? 0 : 1, ev)) return rc;
-    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
+    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
+        const Gs2Plan& P = h->plan2[op];
+        Gs2Args ga;
+        ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
+        ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp;
+        void* args2[] = {&ga};
+        CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
+    } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
         CK(cudaLaunchCooperativeKernel(pick_gs(op), dim3(h->grid_gs[op]), dim3(h->wf_threads), args, h->wf_smem, h->stream));
     } else {
         if (h->p.sweep_order == SRCFD_ORDER_RED_BLACK && op == OP_QUICK)
@@ -575,6 +639,27 @@ int srcfd_k_solve_momentum(srcfd_handle* h, int k, int scheme, int32_t* sweeps, 
 }
 int srcfd_k_implicit_solve(srcfd_handle* h) { CKH(h); return l_implicit_solve(h); }
 
+int srcfd_timer_start(srcfd_handle* h) {
+    CKH(h);
+    if (!h->tm_a) { CK(cudaEventCreate(&h->tm_a)); CK(cudaEventCreate(&h->tm_b)); }
+    CK(cudaEventRecord(h->tm_a, h->stream));
+    return SRCFD_OK;
+}
+int srcfd_timer_stop(srcfd_handle* h, double* ms) {
+    CKH(h);
+    if (!h->tm_a || !ms) return fail(SRCFD_ERR_ARG, "timer not started / null out");
+    CK(cudaEventRecord(h->tm_b, h->stream));
+    CK(cudaEventSynchronize(h->tm_b));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->tm_a, h->tm_b));
+    *ms = f;
+    return SRCFD_OK;
+}
+int srcfd_debug_read(srcfd_handle* h, double* out, int64_t n) {   // debug builds: raw doubles stored behind the scratch plane
+    CKH(h);
+    CK(cudaMemcpy(out, h->scratch + h->K.plane + 64, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return SRCFD_OK;
+}
 int srcfd_launch_count(srcfd_handle* h, int64_t* launches) {
     if (!h || !launches) return fail(SRCFD_ERR_ARG, "null argument");
     *launches = h->launches;

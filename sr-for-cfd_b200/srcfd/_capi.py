@@ -55,7 +55,7 @@ SYMBOLS = [
     "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
     "srcfd_k_solve_pressure", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
-    "srcfd_timing_enable", "srcfd_timing_read",
+    "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
 ]
 
 
@@ -222,6 +222,14 @@ class Handle:
         n = C.c_int64(0)
         check(lib().srcfd_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def timer_start(self):
+        check(lib().srcfd_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        check(lib().srcfd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def timing_enable(self, on=True):
         check(lib().srcfd_timing_enable(self._h, C.c_int(int(on))))
