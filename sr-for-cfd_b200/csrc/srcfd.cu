@@ -63,6 +63,8 @@ struct srcfd_handle {
     Gs2Plan plan2[3];
     int grid_gs2[3] = {0, 0, 0};
     double* halo = nullptr;
+    long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
+    size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
     int inner_cap = 0;          // capacity of the per-sweep buffers (inner_max at creation)
     int guess_bias = 0;
@@ -127,18 +129,21 @@ static const void* pick_gs2(int op) {
     if (op == OP_UPWIND) return gs2_kernel<OP_UPWIND>();
     return gs2_kernel<OP_QUICK>();
 }
-template <int OP> static void shape2(int& K, int& NB, int& MAXT) { K = Wf2Shape<OP>::K; NB = Wf2Shape<OP>::NB; MAXT = Wf2Shape<OP>::MAXT; }
+template <int OP> static void shape2(int& K, int& NB, int& MAXT, int& NAUX, int& AD) {
+    K = Wf2Shape<OP>::K; NB = Wf2Shape<OP>::NB; MAXT = Wf2Shape<OP>::MAXT; NAUX = Wf2Shape<OP>::NAUX; AD = Wf2Shape<OP>::AD;
+}
 
 // Row bands for the K-sweep wavefront: (K+1) thread groups of RS slots each (+ service warps) must fit the
 // CTA, and every band needs >= NB*K rows so that the redundant rows of the band above stay inside it.
 static int plan_gs2(srcfd_handle* h, int op) {
-    int K, NB, MAXT;
-    if (op == OP_PRESSURE) shape2<OP_PRESSURE>(K, NB, MAXT);
-    else if (op == OP_UPWIND) shape2<OP_UPWIND>(K, NB, MAXT);
-    else shape2<OP_QUICK>(K, NB, MAXT);
+    int K, NB, MAXT, NAUX, AD;
+    if (op == OP_PRESSURE) shape2<OP_PRESSURE>(K, NB, MAXT, NAUX, AD);
+    else if (op == OP_UPWIND) shape2<OP_UPWIND>(K, NB, MAXT, NAUX, AD);
+    else shape2<OP_QUICK>(K, NB, MAXT, NAUX, AD);
     const int nx = h->p.nx;
-    const int rs_max = ((MAXT - WF_SVC) / (K + 1)) / 32 * 32;          // slots per group, warp multiple
-    const int rows_max = rs_max - NB * K - 2;                           // band rows that fit
+    const int rs_max = ((MAXT - WF_SVC - 32) / (K + 1)) / 32 * 32;     // slots per group, warp multiple (32: edge warp)
+    int rows_max = rs_max - NB * K - 2;                                 // band rows that fit
+    if (const char* e = getenv("SRCFD_BAND_ROWS")) { const int v = atoi(e); if (v >= NB * K && v < rows_max) rows_max = v; }
     Gs2Plan& P = h->plan2[op];
     P.K = K;
     int nb = (nx + rows_max - 1) / rows_max;
@@ -151,9 +156,9 @@ static int plan_gs2(srcfd_handle* h, int op) {
         if (nb > nx) return fail(SRCFD_ERR_ARG, "cannot band the grid for the wavefront kernel");
     }
     P.RS = ((P.band_rows + NB * K + 2 + 31) / 32) * 32;
-    P.ncomp = (K + 1) * P.RS;
+    P.ncomp = (K + 1) * P.RS + 32;
     P.nthreads = P.ncomp + WF_SVC;
-    P.smem = sizeof(double) * (size_t)(WF2_RING + 1) * P.ncomp;
+    P.smem = sizeof(double) * ((size_t)(WF2_RING + 1) * P.ncomp + (size_t)NAUX * AD * P.RS);
     if (P.nthreads > MAXT) return fail(SRCFD_ERR_ARG, "wavefront plan exceeds the CTA size");
     int occ = 0;
     CK(cudaFuncSetAttribute(pick_gs2(op), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
@@ -211,7 +216,7 @@ int srcfd_destroy(srcfd_handle* h) {
     for (auto& e : h->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
-    cudaFree(h->staging); cudaFree(h->halo);
+    cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -253,6 +258,11 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     int maxbands = h->nbands;
     for (int op = 0; op < 3; ++op) { maxbands = std::max(maxbands, h->plan2[op].nbands); gmax = std::max(gmax, h->grid_gs2[op]); }
     h->n_partials = std::max((size_t)h->inner_cap * maxbands, (size_t)2 * gmax) + 64;
+    if (getenv("SRCFD_TRACE")) {
+        h->trace_n = (size_t)(h->inner_cap / 4 + 2) * maxbands * 8;
+        CKB(cudaMalloc(&h->trace, sizeof(long long) * h->trace_n));
+        CKB(cudaMemsetAsync(h->trace, 0, sizeof(long long) * h->trace_n, h->stream));
+    }
     CKB(cudaMalloc(&h->halo, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64));
     CKB(cudaMemsetAsync(h->halo, 0, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64, h->stream));
     CKB(cudaMalloc(&h->partials, sizeof(double) * h->n_partials));
@@ -423,6 +433,8 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
         const Gs2Plan& P = h->plan2[op];
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
+        ga.trace = h->trace;
+        ga.dbg_skip = getenv("SRCFD_DBG_SKIP") ? atoi(getenv("SRCFD_DBG_SKIP")) : 0;
         ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp;
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
@@ -658,6 +670,13 @@ int srcfd_timer_stop(srcfd_handle* h, double* ms) {
 int srcfd_debug_read(srcfd_handle* h, double* out, int64_t n) {   // debug builds: raw doubles stored behind the scratch plane
     CKH(h);
     CK(cudaMemcpy(out, h->scratch + h->K.plane + 64, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return SRCFD_OK;
+}
+int srcfd_trace_read(srcfd_handle* h, long long* out, int64_t n) {   // SRCFD_TRACE=1 only
+    CKH(h);
+    if (!h->trace) return fail(SRCFD_ERR_ARG, "tracing is off (set SRCFD_TRACE=1 before creating the handle)");
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->trace, sizeof(long long) * std::min<size_t>(n, h->trace_n), cudaMemcpyDeviceToHost));
     return SRCFD_OK;
 }
 int srcfd_launch_count(srcfd_handle* h, int64_t* launches) {
