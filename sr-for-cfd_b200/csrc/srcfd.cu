@@ -434,7 +434,6 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
         ga.trace = h->trace;
-        ga.dbg_skip = getenv("SRCFD_DBG_SKIP") ? atoi(getenv("SRCFD_DBG_SKIP")) : 0;
         ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp;
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));

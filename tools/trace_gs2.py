@@ -24,12 +24,21 @@ tr = tr[: ngroups * B].reshape(ngroups, B, 8)
 t0 = tr[:, :, 0].min()
 start, first, end, wait, steps = [tr[:, :, i] for i in range(5)]
 print(f"bands={B} groups={ngroups} total={(end.max() - t0) / 1e3:.1f} us")
+print(f"publishes per task: mean {tr[:, :, 6].mean():.1f}; max step gap between publishes: mean {tr[:, :, 7].mean():.1f} max {tr[:, :, 7].max()}")
 run = (end - first) / 1e3
 print(f"task run time (first step..end): mean {run.mean():.1f} us; waited inside: mean {wait.mean() / 1e3:.1f} us; steps {steps[0, 0]}")
 print(f"=> busy step time {(run.mean() - wait.mean() / 1e3) / steps[0, 0] * 1e3:.0f} ns/step; idle before first step: mean {((first - start) / 1e3).mean():.1f} us")
 g = np.diff(first[:, 0]) / 1e3
 print(f"group-to-group start lag (band 0): mean {g.mean():.1f} us, min {g.min():.1f}, max {g.max():.1f}")
+t53 = tr[:, :, 5]
 for b in range(1, B):
+    hop = (first[:, b] - t53[:, b - 1]) / 1e3
+    print(f"  hop: band {b} first step - band {b-1} reached the step that allows it: mean {hop.mean():.1f} us  median {np.median(hop):.1f} min {hop.min():.1f}")
     d = (first[:, b] - first[:, b - 1]) / 1e3
     print(f"band {b} starts {d.mean():.1f} us after band {b - 1}")
 print("first 3 groups, band 0: start/first/end (us):", [(round((start[i, 0] - t0) / 1e3, 1), round((first[i, 0] - t0) / 1e3, 1), round((end[i, 0] - t0) / 1e3, 1)) for i in range(3)])
+if len(sys.argv) > 3:
+    g0 = int(sys.argv[3])
+    for g_ in range(g0, min(g0 + 3, ngroups)):
+        for b_ in range(B):
+            print(f"grp {g_} band {b_}: picked {(start[g_, b_] - t0) / 1e3:8.1f}  first {(first[g_, b_] - t0) / 1e3:8.1f}  end {(end[g_, b_] - t0) / 1e3:8.1f}  waited {wait[g_, b_] / 1e3:6.1f}  sm {tr[g_, b_, 5]}")
