@@ -125,6 +125,25 @@ int srcfd_timing_enable(srcfd_handle *h, int enabled);
 int srcfd_timing_read(srcfd_handle *h, double *pressure_ms, int64_t *pressure_launches,
                       double *momentum_ms, int64_t *momentum_launches);
 
+/* ---- SR autoencoder inference (encoder_10 + decoder_400, sr-ae-conv.ipynb cell 162-169 / 277-287) ----
+ * Replaces tf.keras load_model(...).predict at PyCFD_ML_accelerated.py:831-858.  float32, NHWC, kernels and
+ * biases passed in their Keras layouts (Conv2D (kh,kw,Cin,Cout), Conv2DTranspose (kh,kw,Cout,Cin), Dense (in,out)). */
+typedef struct srcfd_sr srcfd_sr;
+const char *srcfd_sr_last_error(void);
+int srcfd_sr_create(int device, srcfd_sr **out);
+int srcfd_sr_destroy(srcfd_sr *h);
+/* layers in order: conv2d, conv2d_1, dense, latent_vector */
+int srcfd_sr_set_encoder(srcfd_sr *h, const float *const kernels[4], const float *const biases[4]);
+/* layers in order: dense, conv2d_transpose, _1, _2, _3, _4, output_image_400 */
+int srcfd_sr_set_decoder(srcfd_sr *h, const float *const kernels[7], const float *const biases[7]);
+int srcfd_sr_encode(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float *z /* (B,50) */);
+int srcfd_sr_decode(srcfd_sr *h, const float *z /* (B,50) */, int B, float *out /* (B,400,400,1) */);
+/* SuperResolutionAE.call (PyCFD_ML_accelerated.py:686-689) */
+int srcfd_sr_predict(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float *out /* (B,400,400,1) */);
+/* decoder on device-resident latents/outputs (cudaMalloc'ed by the caller); *ms = CUDA-event time of the batch */
+int srcfd_sr_decode_device(srcfd_sr *h, uint64_t z_dev, int B, uint64_t out_dev, double *ms);
+int srcfd_sr_launch_count(srcfd_sr *h, int64_t *launches);
+
 #define SRCFD_OK 0
 #define SRCFD_ERR_ARG 1
 #define SRCFD_ERR_CUDA 2

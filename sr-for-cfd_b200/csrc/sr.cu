@@ -1,0 +1,306 @@
+// sr.cu -- SR autoencoder inference (encoder_10 + decoder_400) behind the C ABI of include/srcfd.h.
+// Architecture: sr-ae-conv.ipynb cell lines 162-169 (encoder) and 277-287 (decoder); call sites
+// PyCFD_ML_accelerated.py:831-858.  NHWC float32 like Keras; kernel layouts are converted once at
+// upload so that the output-channel index is the contiguous (coalesced) one.
+//
+// This file holds the fp32 CUDA-core path: every layer is one kernel, one thread per output element
+// (output channel fastest => weight reads coalesced, activation reads broadcast).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/srcfd.h"
+
+namespace {
+
+thread_local std::string g_sr_err;
+int sr_fail(int code, const std::string& m) { g_sr_err = m; return code; }
+#define SRCK(call)                                                                                     \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return sr_fail(SRCFD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+
+// out[b, n] = act(in[b, :] . W[:, n] + bias[n]);  W is (K, N) row-major (Keras Dense layout)
+__global__ void k_dense(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                        float* __restrict__ out, int B, int K, int N, int act) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * N) return;
+    const int n = (int)(t % N), b = (int)(t / N);
+    const float* x = in + (long long)b * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(x[k], W[(long long)k * N + n], acc);
+    acc += bias[n];
+    out[t] = act ? swishf(acc) : acc;
+}
+
+// Conv2D, cross-correlation, zero padding (pt, pl) at the top/left; W (kh, kw, Cin, Cout)
+__global__ void k_conv2d(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                         float* __restrict__ out, int B, int H, int Wd, int Cin, int OH, int OW, int Cout, int kh, int kw,
+                         int stride, int pt, int pl, int act) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * OH * OW * Cout) return;
+    const int co = (int)(t % Cout);
+    long long p = t / Cout;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+        const int iy = oy * stride + ky - pt;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < kw; ++kx) {
+            const int ix = ox * stride + kx - pl;
+            if (ix < 0 || ix >= Wd) continue;
+            const float* x = in + (((long long)b * H + iy) * Wd + ix) * Cin;
+            const float* w = W + ((long long)(ky * kw + kx) * Cin) * Cout + co;
+            for (int ci = 0; ci < Cin; ++ci) acc = fmaf(x[ci], w[(long long)ci * Cout], acc);
+        }
+    }
+    acc += bias[co];
+    out[t] = act ? swishf(acc) : acc;
+}
+
+// Conv2DTranspose 'valid' in gather form; Wt (kh, kw, Cin, Cout) (= Keras (kh, kw, Cout, Cin) transposed at upload)
+__global__ void k_conv2d_transpose(const float* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                   float* __restrict__ out, int B, int H, int Wd, int Cin, int OH, int OW, int Cout, int k,
+                                   int stride, int act) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * OH * OW * Cout) return;
+    const int co = (int)(t % Cout);
+    long long p = t / Cout;
+    const int X = (int)(p % OW); p /= OW;
+    const int Y = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float acc = 0.f;
+    for (int ky = Y % stride; ky < k; ky += stride) {
+        const int y = (Y - ky) / stride;
+        if (y < 0 || y >= H) continue;
+        for (int kx = X % stride; kx < k; kx += stride) {
+            const int x = (X - kx) / stride;
+            if (x < 0 || x >= Wd) continue;
+            const float* xin = in + (((long long)b * H + y) * Wd + x) * Cin;
+            const float* w = Wt + ((long long)(ky * k + kx) * Cin) * Cout + co;
+            for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xin[ci], w[(long long)ci * Cout], acc);
+        }
+    }
+    acc += bias[co];
+    out[t] = act ? swishf(acc) : acc;
+}
+
+struct Layer { float* W = nullptr; float* b = nullptr; };
+
+}  // namespace
+
+struct srcfd_sr {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    Layer enc[4], dec[7];
+    bool has_enc = false, has_dec = false;
+    float* act[8] = {nullptr};      // activation buffers for one chunk
+    float *zin = nullptr, *xin = nullptr;
+    int chunk = 0;
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    int64_t launches = 0;
+};
+
+namespace {
+
+const int DEC_ACT_ELEMS[7] = {12 * 12 * 256, 25 * 25 * 128, 50 * 50 * 64, 100 * 100 * 32, 200 * 200 * 16, 400 * 400 * 8, 400 * 400};
+
+int upload(float** dst, const float* src, size_t n, cudaStream_t s) {
+    if (!*dst) SRCK(cudaMalloc(dst, n * sizeof(float)));
+    SRCK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    return SRCFD_OK;
+}
+// Keras Conv2DTranspose kernel (kh,kw,Cout,Cin) -> (kh,kw,Cin,Cout)
+std::vector<float> transpose_last2(const float* k, int taps, int Cout, int Cin) {
+    std::vector<float> o((size_t)taps * Cin * Cout);
+    for (int t = 0; t < taps; ++t)
+        for (int co = 0; co < Cout; ++co)
+            for (int ci = 0; ci < Cin; ++ci) o[((size_t)t * Cin + ci) * Cout + co] = k[((size_t)t * Cout + co) * Cin + ci];
+    return o;
+}
+int ensure_chunk(srcfd_sr* h, int chunk) {
+    if (h->chunk >= chunk) return SRCFD_OK;
+    for (int i = 0; i < 8; ++i) { cudaFree(h->act[i]); h->act[i] = nullptr; }
+    cudaFree(h->zin); cudaFree(h->xin); h->zin = h->xin = nullptr;
+    for (int i = 0; i < 7; ++i) SRCK(cudaMalloc(&h->act[i], (size_t)chunk * DEC_ACT_ELEMS[i] * sizeof(float)));
+    SRCK(cudaMalloc(&h->act[7], (size_t)chunk * 3200 * sizeof(float)));   // encoder scratch (5*5*128)
+    SRCK(cudaMalloc(&h->zin, (size_t)chunk * 192 * sizeof(float)));   // (chunk,128) dense scratch + (chunk,50) latents
+    SRCK(cudaMalloc(&h->xin, (size_t)chunk * 1600 * sizeof(float)));
+    h->chunk = chunk;
+    return SRCFD_OK;
+}
+inline int nblk(long long n) { return (int)((n + 255) / 256); }
+
+// encoder on `B` samples: x_dev (B,10,10,1) -> z_dev (B,50)
+int run_encoder(srcfd_sr* h, const float* x_dev, int B, float* z_dev) {
+    float* a0 = h->xin;          // (B,5,5,64)
+    float* a1 = h->act[7];       // (B,5,5,128)
+    float* a2 = h->zin;          // (B,128)
+    k_conv2d<<<nblk((long long)B * 25 * 64), 256, 0, h->stream>>>(x_dev, h->enc[0].W, h->enc[0].b, a0, B, 10, 10, 1, 5, 5, 64, 3, 3, 2, 0, 0, 1);
+    k_conv2d<<<nblk((long long)B * 25 * 128), 256, 0, h->stream>>>(a0, h->enc[1].W, h->enc[1].b, a1, B, 5, 5, 64, 5, 5, 128, 3, 3, 1, 1, 1, 1);
+    k_dense<<<nblk((long long)B * 128), 256, 0, h->stream>>>(a1, h->enc[2].W, h->enc[2].b, a2, B, 3200, 128, 1);
+    k_dense<<<nblk((long long)B * 50), 256, 0, h->stream>>>(a2, h->enc[3].W, h->enc[3].b, z_dev, B, 128, 50, 0);
+    h->launches += 4;
+    SRCK(cudaGetLastError());
+    return SRCFD_OK;
+}
+// decoder on `B` samples: z_dev (B,50) -> out_dev (B,400,400,1)
+int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
+    k_dense<<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
+    const int hw[6] = {12, 25, 50, 100, 200, 400}, ch[6] = {256, 128, 64, 32, 16, 8};
+    for (int l = 0; l < 5; ++l) {
+        const int k = (l == 0) ? 3 : 2;
+        k_conv2d_transpose<<<nblk((long long)B * hw[l + 1] * hw[l + 1] * ch[l + 1]), 256, 0, h->stream>>>(
+            h->act[l], h->dec[l + 1].W, h->dec[l + 1].b, h->act[l + 1], B, hw[l], hw[l], ch[l], hw[l + 1], hw[l + 1], ch[l + 1], k, 2, 1);
+    }
+    k_conv2d<<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
+    h->launches += 7;
+    SRCK(cudaGetLastError());
+    return SRCFD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* srcfd_sr_last_error(void) { return g_sr_err.c_str(); }
+
+int srcfd_sr_create(int device, srcfd_sr** out) {
+    if (!out) return sr_fail(SRCFD_ERR_ARG, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return sr_fail(SRCFD_ERR_CUDA, "no CUDA device: libsrcfd has no CPU fallback");
+    if (device < 0 || device >= ndev) return sr_fail(SRCFD_ERR_ARG, "bad device ordinal");
+    srcfd_sr* h = new srcfd_sr();
+    h->dev = device;
+    SRCK(cudaSetDevice(device));
+    SRCK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    SRCK(cudaEventCreate(&h->ea)); SRCK(cudaEventCreate(&h->eb));
+    *out = h;
+    return SRCFD_OK;
+}
+
+int srcfd_sr_destroy(srcfd_sr* h) {
+    if (!h) return SRCFD_OK;
+    cudaSetDevice(h->dev);
+    cudaStreamSynchronize(h->stream);
+    for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
+    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); }
+    for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
+    cudaFree(h->zin); cudaFree(h->xin);
+    cudaEventDestroy(h->ea); cudaEventDestroy(h->eb);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return SRCFD_OK;
+}
+
+// kernels/biases in Keras layouts: conv2d (3,3,1,64), conv2d_1 (3,3,64,128), dense (3200,128), latent_vector (128,50)
+int srcfd_sr_set_encoder(srcfd_sr* h, const float* const kernels[4], const float* const biases[4]) {
+    if (!h || !kernels || !biases) return sr_fail(SRCFD_ERR_ARG, "null argument");
+    SRCK(cudaSetDevice(h->dev));
+    const size_t kn[4] = {3 * 3 * 1 * 64, 3 * 3 * 64 * 128, 3200 * 128, 128 * 50}, bn[4] = {64, 128, 128, 50};
+    for (int i = 0; i < 4; ++i) {
+        if (int rc = upload(&h->enc[i].W, kernels[i], kn[i], h->stream)) return rc;
+        if (int rc = upload(&h->enc[i].b, biases[i], bn[i], h->stream)) return rc;
+    }
+    SRCK(cudaStreamSynchronize(h->stream));
+    h->has_enc = true;
+    return SRCFD_OK;
+}
+
+// kernels/biases in Keras layouts: dense (50,36864); conv2d_transpose (3,3,128,256), _1 (2,2,64,128), _2 (2,2,32,64),
+// _3 (2,2,16,32), _4 (2,2,8,16); output_image_400 (3,3,8,1)
+int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float* const biases[7]) {
+    if (!h || !kernels || !biases) return sr_fail(SRCFD_ERR_ARG, "null argument");
+    SRCK(cudaSetDevice(h->dev));
+    const int cin[5] = {256, 128, 64, 32, 16}, cout[5] = {128, 64, 32, 16, 8}, taps[5] = {9, 4, 4, 4, 4};
+    if (int rc = upload(&h->dec[0].W, kernels[0], (size_t)50 * 36864, h->stream)) return rc;
+    if (int rc = upload(&h->dec[0].b, biases[0], 36864, h->stream)) return rc;
+    for (int l = 0; l < 5; ++l) {
+        std::vector<float> wt = transpose_last2(kernels[l + 1], taps[l], cout[l], cin[l]);
+        if (int rc = upload(&h->dec[l + 1].W, wt.data(), wt.size(), h->stream)) return rc;
+        SRCK(cudaStreamSynchronize(h->stream));      // wt is a temporary
+        if (int rc = upload(&h->dec[l + 1].b, biases[l + 1], cout[l], h->stream)) return rc;
+    }
+    if (int rc = upload(&h->dec[6].W, kernels[6], 3 * 3 * 8 * 1, h->stream)) return rc;
+    if (int rc = upload(&h->dec[6].b, biases[6], 1, h->stream)) return rc;
+    SRCK(cudaStreamSynchronize(h->stream));
+    h->has_dec = true;
+    return SRCFD_OK;
+}
+
+static int sr_run(srcfd_sr* h, const float* x, const float* z, int B, float* zout, float* out) {
+    SRCK(cudaSetDevice(h->dev));
+    const int CH = std::min(B, 32);
+    if (int rc = ensure_chunk(h, CH)) return rc;
+    float* zdev = h->zin + (size_t)h->chunk * 128;   // latents (CH,50) live behind the (chunk,128) dense scratch
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int nb = std::min(CH, B - b0);
+        if (x) {
+            float* xdev = h->act[6];              // reuse the output buffer as input staging (consumed before it is written)
+            SRCK(cudaMemcpyAsync(xdev, x + (size_t)b0 * 100, (size_t)nb * 100 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            if (int rc = run_encoder(h, xdev, nb, zdev)) return rc;
+        } else {
+            SRCK(cudaMemcpyAsync(zdev, z + (size_t)b0 * 50, (size_t)nb * 50 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        }
+        if (zout) SRCK(cudaMemcpyAsync(zout + (size_t)b0 * 50, zdev, (size_t)nb * 50 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (out) {
+            if (int rc = run_decoder(h, zdev, nb, h->act[6])) return rc;
+            SRCK(cudaMemcpyAsync(out + (size_t)b0 * 160000, h->act[6], (size_t)nb * 160000 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        }
+        SRCK(cudaStreamSynchronize(h->stream));
+    }
+    return SRCFD_OK;
+}
+
+// encoder_10.predict: x (B,10,10,1) host -> z (B,50) host
+int srcfd_sr_encode(srcfd_sr* h, const float* x, int B, float* z) {
+    if (!h || !x || !z || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_enc) return sr_fail(SRCFD_ERR_ARG, "encoder weights not set");
+    return sr_run(h, x, nullptr, B, z, nullptr);
+}
+// decoder_400.predict: z (B,50) host -> out (B,400,400,1) host
+int srcfd_sr_decode(srcfd_sr* h, const float* z, int B, float* out) {
+    if (!h || !z || !out || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_dec) return sr_fail(SRCFD_ERR_ARG, "decoder weights not set");
+    return sr_run(h, nullptr, z, B, nullptr, out);
+}
+// SuperResolutionAE.call (PyCFD_ML_accelerated.py:686-689): x (B,10,10,1) host -> (B,400,400,1) host
+int srcfd_sr_predict(srcfd_sr* h, const float* x, int B, float* out) {
+    if (!h || !x || !out || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_enc || !h->has_dec) return sr_fail(SRCFD_ERR_ARG, "encoder/decoder weights not set");
+    return sr_run(h, x, nullptr, B, nullptr, out);
+}
+// Throughput entry: latents and outputs resident in HBM (device pointers), whole batch, CUDA-event timed.
+int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev, double* ms) {
+    if (!h || !z_dev || !out_dev || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_dec) return sr_fail(SRCFD_ERR_ARG, "decoder weights not set");
+    SRCK(cudaSetDevice(h->dev));
+    const int CH = std::min(B, 32);
+    if (int rc = ensure_chunk(h, CH)) return rc;
+    SRCK(cudaEventRecord(h->ea, h->stream));
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int nb = std::min(CH, B - b0);
+        if (int rc = run_decoder(h, (const float*)(uintptr_t)z_dev + (size_t)b0 * 50, nb, (float*)(uintptr_t)out_dev + (size_t)b0 * 160000)) return rc;
+    }
+    SRCK(cudaEventRecord(h->eb, h->stream));
+    SRCK(cudaEventSynchronize(h->eb));
+    float f = 0.f;
+    SRCK(cudaEventElapsedTime(&f, h->ea, h->eb));
+    if (ms) *ms = f;
+    return SRCFD_OK;
+}
+int srcfd_sr_launch_count(srcfd_sr* h, int64_t* n) {
+    if (!h || !n) return sr_fail(SRCFD_ERR_ARG, "null argument");
+    *n = h->launches;
+    return SRCFD_OK;
+}
+
+}  // extern "C"

@@ -56,6 +56,8 @@ SYMBOLS = [
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
     "srcfd_k_solve_pressure", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
+    "srcfd_sr_last_error", "srcfd_sr_create", "srcfd_sr_destroy", "srcfd_sr_set_encoder", "srcfd_sr_set_decoder",
+    "srcfd_sr_encode", "srcfd_sr_decode", "srcfd_sr_predict", "srcfd_sr_decode_device", "srcfd_sr_launch_count",
 ]
 
 

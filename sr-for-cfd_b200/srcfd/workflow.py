@@ -63,6 +63,9 @@ class SuperResolutionAE:
         self.decoder_hr = decoder_hr
 
     def call(self, inputs, training=False):
+        from . import sr
+        if isinstance(self.encoder_lr, sr.Encoder) and isinstance(self.decoder_hr, sr.Decoder):
+            return sr.predict(self.encoder_lr, self.decoder_hr, inputs)      # latents stay on the device
         return self.decoder_hr(self.encoder_lr(inputs))
 
     __call__ = call
