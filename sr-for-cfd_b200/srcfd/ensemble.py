@@ -1,0 +1,128 @@
+"""Re/BC parameter-sweep ensembles (BASELINE.json configs[2]): independent cases sharded over GPUs.
+
+The reference runs its sweep as a serial Python loop (sr-simulation-data-creation.ipynb cell-2 lines
+744-794).  Cases are fully independent, so the multi-GPU path has NO data-path collective: the case list
+is dealt round-robin to the ranks (one process per GPU), each rank runs its share -- several cases
+concurrently on its GPU, each on its own stream with a capped persistent grid -- and rank 0 gathers the
+per-case results at the end.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+@dataclass
+class CaseSpec:
+    """One member of the sweep.  kind: 'ldc' (single lid), 'ldc2' (double lid, u_bottom = 1) or 'bfs'."""
+    kind: str
+    Re: float
+    nx: int = 400
+    ny: int = 400
+    max_iterations: int = 2000
+    warm_start: bool = True
+    name: str = ""
+
+    def label(self):
+        return self.name or f"{self.kind}_Re{self.Re:g}_{self.nx}x{self.ny}"
+
+
+@dataclass
+class CaseResult:
+    label: str
+    rank: int
+    iterations: int
+    converged: bool
+    seconds: float
+    total_sweeps: List[int]
+    rms: List[float]
+    fields: Optional[np.ndarray] = None       # (3, ny, nx) u, v, p in the reference's output orientation
+
+
+def multibc_sweep(res_ldc=tuple(range(50, 701, 50)), res_bfs=(100, 200, 400), nx=400, ny=400, max_iterations=2000):
+    """The multiBC ensemble of SURVEY.md section 8d config 3."""
+    cases = [CaseSpec(k, float(Re), nx, ny, max_iterations) for Re in res_ldc for k in ("ldc", "ldc2")]
+    cases += [CaseSpec("bfs", float(Re), nx, ny, max_iterations) for Re in res_bfs]
+    return cases
+
+
+def shard_cases(cases: Sequence, rank: int, world: int) -> List:
+    """Static round-robin: case i belongs to rank i % world (expected cost is similar across the sweep)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return [c for i, c in enumerate(cases) if i % world == rank]
+
+
+def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optional[dict] = None, keep_fields=True) -> CaseResult:
+    """Coarse solve -> SR warm start -> fine solve for one case on one GPU (the reference's per-case workflow)."""
+    from . import bfs, ldc
+    mod = bfs if spec.kind == "bfs" else ldc
+    wf = mod._wf
+    t0 = time.time()
+    bc = None
+    if spec.kind == "ldc2":
+        bc = ldc.BoundaryConditions()
+        bc.u_boundaries['bottom'] = ldc.BoundaryCondition('dirichlet', 1.0)     # PyCFD_ML_accelerated.py:1387-1392
+    solver = wf._make_solver(spec.Re, spec.nx, spec.ny, *wf._defaults(None, None, None, None)[:2], None,
+                             spec.max_iterations, bc, 1.0, 2.0, 1.0, *wf._defaults(None, None, None, None)[2:], None,
+                             device=device, max_ctas=max_ctas)
+    if spec.warm_start and sr_files is not None:
+        coarse = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=sr_files.get("coarse_iterations", 2000),
+                                          bc=bc, save=False)
+        kw = dict(use_aspect_ratio_correction=True, lx=10.0, ly=3.0) if spec.kind == "bfs" else {}
+        hr = wf.ml_super_resolution(coarse, 10, spec.nx, sr_files["stats"], sr_files["encoder"], sr_files["decoder"], **kw)
+        solver._sync_params()
+        solver._handle.set_fields(np.stack([np.asarray(hr[c], dtype=np.float32) for c in "uvp"]))
+        solver._handle.download(solver.Var, solver.VarOld, solver.Ff)
+    n, _ = solver.solve("ensemble", verbose=False, save=False)
+    st = solver._handle.status()
+    fields = np.stack([solver.Var[k, 1:-1, 1:-1].T for k in range(3)]) if keep_fields else None
+    return CaseResult(spec.label(), -1, int(n), bool(st["converged"]), time.time() - t0,
+                      [int(x) for x in solver.total_sweeps], [float(x) for x in st["rms"]], fields)
+
+
+def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, num_sms: int = 148,
+              runner: Callable = run_case, **kw) -> List[CaseResult]:
+    """Run this rank's cases, `concurrency` at a time, each with 1/concurrency of the SMs."""
+    results: List[Optional[CaseResult]] = [None] * len(cases)
+    lock, nxt = threading.Lock(), [0]
+    max_ctas = max(1, num_sms // max(1, concurrency)) if concurrency > 1 else 0
+
+    def worker():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(cases):
+                return
+            results[i] = runner(cases[i], device=device, max_ctas=max_ctas, **kw)
+
+    threads = [threading.Thread(target=worker) for _ in range(max(1, min(concurrency, len(cases))))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return [r for r in results if r is not None]
+
+
+def run_ensemble(cases: Sequence[CaseSpec], concurrency: int = 2, runner: Callable = run_case, dist=None,
+                 device: Optional[int] = None, **kw) -> Optional[List[CaseResult]]:
+    """Shard `cases` over the ranks of an initialised torch.distributed group (or run them all when there is
+    none) and gather every CaseResult on rank 0 (other ranks return None).  No collective on the data path."""
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None and dist.is_initialized() else (0, 1)
+    mine = shard_cases(list(cases), rank, world)
+    res = run_local(mine, device=rank if device is None else device, concurrency=concurrency, runner=runner, **kw)
+    for r in res:
+        r.rank = rank
+    if world == 1:
+        return res
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(res, gathered, dst=0)
+    if rank != 0:
+        return None
+    order = {c.label(): i for i, c in enumerate(cases)}
+    return sorted([r for part in gathered for r in part], key=lambda r: order[r.label])

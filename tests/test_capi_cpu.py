@@ -1,0 +1,44 @@
+"""No-GPU checks of the boundary: the shared object loads, exports every symbol include/srcfd.h declares, and
+refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from srcfd import _capi as capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "srcfd.h")).read()
+    return sorted(set(re.findall(r"\b(srcfd_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_library_agree():
+    names = _declared()
+    assert len(names) >= 40
+    L = C.CDLL(capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in include/srcfd.h but not exported: {missing}"
+    assert sorted(set(capi.SYMBOLS)) == names, "srcfd/_capi.py SYMBOLS is out of sync with the header"
+    assert L.srcfd_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header():
+    # int32 x2, double x6, int32 + pad, int32[12], double[12], int32 + pad, double x3, int32 + pad, double x3, double,
+    # int32 x4, int32[8]  -> 4-byte members packed with natural alignment
+    assert C.sizeof(capi.Params) == 8 + 48 + 8 + 48 + 96 + 8 + 24 + 8 + 24 + 8 + 16 + 32
+
+
+@pytest.mark.skipif(capi.device_count() > 0, reason="a CUDA device is present")
+def test_no_cpu_fallback():
+    p = capi.Params()
+    p.nx = p.ny = 8
+    p.inner_max = 10
+    with pytest.raises(capi.SrcfdError, match="no CUDA device"):
+        capi.Handle(p)
+    from srcfd import sr
+    with pytest.raises(capi.SrcfdError, match="no CUDA device"):
+        sr.synthetic_decoder(0).predict([[0.0] * 50])

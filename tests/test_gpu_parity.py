@@ -216,3 +216,17 @@ def test_bfs_sir_late_case_type():
     s.solve("x", verbose=False, save=False)
     o = O.OracleSolver(O.bfs_case(10, 10), bfs_at_init=False); o.solve(300)
     assert np.array_equal(s.Var, o.Var)
+
+
+def test_ensemble_concurrent_cases_match_sequential():
+    """Several cases on one GPU at once (own streams, capped persistent grids) give the bits they give alone."""
+    from srcfd import ensemble as E
+    cases = [E.CaseSpec("ldc", 100.0, 48, 40, 6, warm_start=False), E.CaseSpec("ldc2", 300.0, 48, 40, 6, warm_start=False),
+             E.CaseSpec("bfs", 400.0, 48, 40, 6, warm_start=False), E.CaseSpec("ldc", 700.0, 48, 40, 6, warm_start=False)]
+    seq = [E.run_case(c) for c in cases]
+    par = E.run_local(cases, concurrency=3)
+    for a, b in zip(seq, par):
+        assert a.label == b.label and a.iterations == b.iterations and a.total_sweeps == b.total_sweeps
+        assert np.array_equal(a.fields, b.fields)
+    o = O.OracleSolver(O.bfs_case(48, 40)); o.solve(6)
+    assert np.array_equal(par[2].fields, np.stack([o.Var[k, 1:-1, 1:-1].T for k in range(3)]))
