@@ -37,6 +37,8 @@ for p in (ROOT, os.path.join(ROOT, "sr-for-cfd_b200")):
 
 import numpy as np  # noqa: E402
 
+os.environ["NCCL_DEBUG"] = os.environ.get("SRCFD_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+
 NX = NY = 400
 LX, LY = 10.0, 3.0
 DT = 2e-3
@@ -44,6 +46,7 @@ RELAX = {'u': 0.5, 'v': 0.5, 'p': 0.2}
 ENSEMBLE_RE = [400.0, 100.0, 200.0, 300.0, 500.0, 600.0, 700.0, 50.0]
 BYTES_PER_LUP_PRESSURE = 24.0     # read p, read rhs, write p
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+WARM_DESC = "coarse 10x10 solve (2000 its) -> encoder_10 (committed weights) + decoder_400 (synthetic seed-0 weights)"
 
 
 def peaks():
@@ -55,15 +58,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per pressure-solve launch from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_pressure_r01.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
 def warm_start_fields(Re):
     """Coarse 10x10 BFS solve -> SR autoencoder -> (3, ny, nx) float32 initial guess, all on the GPU path
     (bfs_ml_accelerated.py:1310-1517).  Returns (fields, description)."""
-    from srcfd import bfs
+    from srcfd import bfs, sr
     bfs._wf.verbose = False
-    try:
-        from srcfd import sr
-    except ImportError:
-        return None, "zero field (SR module not built)"
+    cache = os.path.join(ROOT, "gpurun_out", f"warm_Re{Re:g}.npy")
+    if os.environ.get("SRCFD_BENCH_WARM_CACHE") and os.path.exists(cache):     # profiling runs: skip the 10x10 coarse solve
+        return np.load(cache), WARM_DESC + " [field cached by the preceding plain run]"
     coarse = bfs.run_coarse_simulation(Re=Re, lr_dim=10, dt=DT, scheme='UPWIND', max_iterations=2000,
                                        relaxation_factors=RELAX, save=False)
     dec = sr.synthetic_decoder(seed=0)
@@ -71,7 +82,7 @@ def warm_start_fields(Re):
                                  os.path.join(GOLDEN, "encoder10_multiBC.h5"), dec,
                                  use_aspect_ratio_correction=True, lx=LX, ly=LY, blend_factor=0.3)
     f = np.stack([np.asarray(hr[c], dtype=np.float32) for c in "uvp"])
-    return f, "coarse 10x10 solve (2000 its) -> encoder_10 (committed weights) + decoder_400 (synthetic seed-0 weights)"
+    return f, WARM_DESC
 
 
 def make_solver(Re, device=0):
@@ -127,8 +138,8 @@ class ClockSampler:
 def cpu_baseline(Re, fields, steps, threads=None):
     """The oracle port on the host cores: `steps` outer iterations of the SAME workload (bounded sample)."""
     from oracle import oracle as O
-    if threads:
-        O.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     case = O.bfs_case(NX, NY, Re=Re, dt=DT, scheme="UPWIND", lx=LX, ly=LY, relax=(0.5, 0.5, 0.2),
                       order=O.ORDER_GS_OMP if cores > 1 else O.ORDER_GS_LEX)
@@ -283,7 +294,7 @@ def run_ours(args):
     p_lups = cells * float(sweeps[2])
     p_ms = tr["pressure_ms"]
     achieved = BYTES_PER_LUP_PRESSURE * p_lups / (p_ms * 1e-3) / 1e9 if p_ms > 0 else 0.0
-    cb = cpu_baseline(Re, fields, 3) if world >= 1 and not args.no_cpu else None
+    cb = cpu_baseline(Re, fields, 3) if world == 1 and not args.no_cpu else None
     line = {
         "metric": "fine-grid cell-updates/s", "value": tot_lup / (t_ms * 1e-3) / 1e9, "unit": "GLUP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
@@ -297,7 +308,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_solve_gs<pressure> (solve_pressure inner loop)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": ncu_traffic(),
                      "algorithmic_bytes_per_launch": BYTES_PER_LUP_PRESSURE * p_lups / max(1, tr["pressure_launches"]),
                      "launches": tr["pressure_launches"], "avg_launch_ms": p_ms / max(1, tr["pressure_launches"]),
                      "share_of_step": p_ms / t_ms if t_ms else None,
