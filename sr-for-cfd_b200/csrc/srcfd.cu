@@ -136,37 +136,45 @@ template <int OP> static void shape2(int& K, int& NB, int& MAXT, int& NAUX, int&
 // Row bands for the K-sweep wavefront: (K+1) thread groups of RS slots each (+ service warps) must fit the
 // CTA, and every band needs >= NB*K rows so that the redundant rows of the band above stay inside it.
 static int plan_gs2(srcfd_handle* h, int op) {
-    int K, NB, MAXT, NAUX, AD;
-    if (op == OP_PRESSURE) shape2<OP_PRESSURE>(K, NB, MAXT, NAUX, AD);
-    else if (op == OP_UPWIND) shape2<OP_UPWIND>(K, NB, MAXT, NAUX, AD);
-    else shape2<OP_QUICK>(K, NB, MAXT, NAUX, AD);
+    int KT, NB, MAXT, NAUX, AD;
+    if (op == OP_PRESSURE) shape2<OP_PRESSURE>(KT, NB, MAXT, NAUX, AD);
+    else if (op == OP_UPWIND) shape2<OP_UPWIND>(KT, NB, MAXT, NAUX, AD);
+    else shape2<OP_QUICK>(KT, NB, MAXT, NAUX, AD);
     const int nx = h->p.nx;
-    const int rs_max = ((MAXT - WF_SVC - 32) / (K + 1)) / 32 * 32;     // slots per group, warp multiple (32: edge warp)
-    int rows_max = rs_max - NB * K - 2;                                 // band rows that fit
-    if (const char* e = getenv("SRCFD_BAND_ROWS")) { const int v = atoi(e); if (v >= NB * K && v < rows_max) rows_max = v; }
     Gs2Plan& P = h->plan2[op];
-    P.K = K;
-    int nb = (nx + rows_max - 1) / rows_max;
-    // prefer more, shorter bands while that still fills the GPU no further than its SM count allows
-    for (;; ++nb) {
-        const int br = (nx + nb - 1) / nb;
-        const int nbe = (nx + br - 1) / br;
-        const int last = nx - (nbe - 1) * br;
-        if (br <= rows_max && (nbe == 1 || last >= NB * K)) { P.band_rows = br; P.nbands = nbe; break; }
-        if (nb > nx) return fail(SRCFD_ERR_ARG, "cannot band the grid for the wavefront kernel");
+    int kmax = KT;
+    if (const char* e = getenv(op == OP_PRESSURE ? "SRCFD_K_PRESSURE" : "SRCFD_K_MOMENTUM")) kmax = std::max(1, std::min(KT, atoi(e)));
+    // Largest K (sweeps per group) whose banding works: every band needs >= NB*K rows so that the redundant rows
+    // of the band above stay inside it, and (K+1) groups of RS slots + edge + service warps must fit the CTA.
+    for (int K = kmax; K >= 1; --K) {
+        const int edge = ((4 * K + 31) / 32) * 32;
+        const int rs_max = ((MAXT - WF_SVC - edge) / (K + 1)) / 32 * 32;
+        int rows_max = rs_max - NB * K - 2;
+        if (rows_max < 1) continue;
+        if (const char* e = getenv("SRCFD_BAND_ROWS")) { const int v = atoi(e); if (v >= NB * K && v < rows_max) rows_max = v; }
+        bool ok = false;
+        for (int nb = (nx + rows_max - 1) / rows_max; nb <= nx; ++nb) {
+            const int br = (nx + nb - 1) / nb;
+            const int nbe = (nx + br - 1) / br;
+            const int last = nx - (nbe - 1) * br;
+            if (br <= rows_max && (nbe == 1 || last >= NB * K)) { P.band_rows = br; P.nbands = nbe; ok = true; break; }
+        }
+        if (!ok) continue;
+        P.K = K;
+        P.RS = ((P.band_rows + NB * K + 2 + 31) / 32) * 32;
+        P.ncomp = (K + 1) * P.RS + edge;
+        P.nthreads = P.ncomp + WF_SVC;
+        P.smem = sizeof(double) * ((size_t)(WF2_RING + 1) * P.ncomp + (size_t)NAUX * AD * P.RS);
+        if (P.nthreads > MAXT) continue;
+        int occ = 0;
+        CK(cudaFuncSetAttribute(pick_gs2(op), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_gs2(op), P.nthreads, P.smem));
+        if (occ < 1) continue;
+        const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+        h->grid_gs2[op] = std::max(1, std::min(cap, occ * h->num_sms));
+        return SRCFD_OK;
     }
-    P.RS = ((P.band_rows + NB * K + 2 + 31) / 32) * 32;
-    P.ncomp = (K + 1) * P.RS + 32;
-    P.nthreads = P.ncomp + WF_SVC;
-    P.smem = sizeof(double) * ((size_t)(WF2_RING + 1) * P.ncomp + (size_t)NAUX * AD * P.RS);
-    if (P.nthreads > MAXT) return fail(SRCFD_ERR_ARG, "wavefront plan exceeds the CTA size");
-    int occ = 0;
-    CK(cudaFuncSetAttribute(pick_gs2(op), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_gs2(op), P.nthreads, P.smem));
-    if (occ < 1) return fail(SRCFD_ERR_CUDA, "K-sweep wavefront kernel does not fit on an SM");
-    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
-    h->grid_gs2[op] = std::max(1, std::min(cap, occ * h->num_sms));
-    return SRCFD_OK;
+    return fail(SRCFD_ERR_ARG, "cannot band the grid for the wavefront kernel");
 }
 
 static int plan_launches(srcfd_handle* h) {
@@ -434,7 +442,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
         ga.trace = h->trace;
-        ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp;
+        ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp; ga.K = P.K;
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
