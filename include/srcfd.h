@@ -142,6 +142,11 @@ int srcfd_sr_decode(srcfd_sr *h, const float *z /* (B,50) */, int B, float *out 
 int srcfd_sr_predict(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float *out /* (B,400,400,1) */);
 /* decoder on device-resident latents/outputs (cudaMalloc'ed by the caller); *ms = CUDA-event time of the batch */
 int srcfd_sr_decode_device(srcfd_sr *h, uint64_t z_dev, int B, uint64_t out_dev, double *ms);
+/* 0 = fp32 CUDA cores (default; the parity path), 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers */
+int srcfd_sr_set_precision(srcfd_sr *h, int mode);
+int srcfd_sr_tc_error(srcfd_sr *h, int *flag);
+/* one tensor-core ConvT layer (1..4) in isolation, host fp32 in/out (operands rounded to bf16): parity tests */
+int srcfd_sr_debug_convT_tc(srcfd_sr *h, int layer, const float *in, int B, float *out);
 int srcfd_sr_launch_count(srcfd_sr *h, int64_t *launches);
 
 #define SRCFD_OK 0

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "../../include/srcfd.h"
+#include "sr_tc.cuh"
 
 namespace {
 
@@ -39,7 +40,13 @@ __global__ void k_dense(const float* __restrict__ in, const float* __restrict__ 
 }
 
 // Conv2D, cross-correlation, zero padding (pt, pl) at the top/left; W (kh, kw, Cin, Cout)
-__global__ void k_conv2d(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+template <typename TIN>
+__device__ __forceinline__ float ld_act(const TIN* p) { return (float)*p; }
+template <>
+__device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TIN>
+__global__ void k_conv2d(const TIN* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                          float* __restrict__ out, int B, int H, int Wd, int Cin, int OH, int OW, int Cout, int kh, int kw,
                          int stride, int pt, int pl, int act) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,9 +63,9 @@ __global__ void k_conv2d(const float* __restrict__ in, const float* __restrict__
         for (int kx = 0; kx < kw; ++kx) {
             const int ix = ox * stride + kx - pl;
             if (ix < 0 || ix >= Wd) continue;
-            const float* x = in + (((long long)b * H + iy) * Wd + ix) * Cin;
+            const TIN* x = in + (((long long)b * H + iy) * Wd + ix) * Cin;
             const float* w = W + ((long long)(ky * kw + kx) * Cin) * Cout + co;
-            for (int ci = 0; ci < Cin; ++ci) acc = fmaf(x[ci], w[(long long)ci * Cout], acc);
+            for (int ci = 0; ci < Cin; ++ci) acc = fmaf(ld_act<TIN>(x + ci), w[(long long)ci * Cout], acc);
         }
     }
     acc += bias[co];
@@ -92,7 +99,7 @@ __global__ void k_conv2d_transpose(const float* __restrict__ in, const float* __
     out[t] = act ? swishf(acc) : acc;
 }
 
-struct Layer { float* W = nullptr; float* b = nullptr; };
+struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; };
 
 }  // namespace
 
@@ -106,6 +113,9 @@ struct srcfd_sr {
     int chunk = 0;
     cudaEvent_t ea = nullptr, eb = nullptr;
     int64_t launches = 0;
+    int precision = 0;                 // 0: fp32 CUDA cores everywhere; 1: bf16 tcgen05 for the four 2x2/stride-2 ConvT layers
+    __nv_bfloat16* actbf[6] = {nullptr};   // bf16 activations of layers 1..5 (index = layer) for one chunk
+    int* tc_err = nullptr;
 };
 
 namespace {
@@ -133,6 +143,8 @@ int ensure_chunk(srcfd_sr* h, int chunk) {
     SRCK(cudaMalloc(&h->act[7], (size_t)chunk * 3200 * sizeof(float)));   // encoder scratch (5*5*128)
     SRCK(cudaMalloc(&h->zin, (size_t)chunk * 192 * sizeof(float)));   // (chunk,128) dense scratch + (chunk,50) latents
     SRCK(cudaMalloc(&h->xin, (size_t)chunk * 1600 * sizeof(float)));
+    for (int i = 1; i < 6; ++i) { cudaFree(h->actbf[i]); SRCK(cudaMalloc(&h->actbf[i], (size_t)chunk * DEC_ACT_ELEMS[i] * sizeof(__nv_bfloat16))); }
+    if (!h->tc_err) { SRCK(cudaMalloc(&h->tc_err, sizeof(int))); SRCK(cudaMemset(h->tc_err, 0, sizeof(int))); }
     h->chunk = chunk;
     return SRCFD_OK;
 }
@@ -143,25 +155,62 @@ int run_encoder(srcfd_sr* h, const float* x_dev, int B, float* z_dev) {
     float* a0 = h->xin;          // (B,5,5,64)
     float* a1 = h->act[7];       // (B,5,5,128)
     float* a2 = h->zin;          // (B,128)
-    k_conv2d<<<nblk((long long)B * 25 * 64), 256, 0, h->stream>>>(x_dev, h->enc[0].W, h->enc[0].b, a0, B, 10, 10, 1, 5, 5, 64, 3, 3, 2, 0, 0, 1);
-    k_conv2d<<<nblk((long long)B * 25 * 128), 256, 0, h->stream>>>(a0, h->enc[1].W, h->enc[1].b, a1, B, 5, 5, 64, 5, 5, 128, 3, 3, 1, 1, 1, 1);
+    k_conv2d<float><<<nblk((long long)B * 25 * 64), 256, 0, h->stream>>>(x_dev, h->enc[0].W, h->enc[0].b, a0, B, 10, 10, 1, 5, 5, 64, 3, 3, 2, 0, 0, 1);
+    k_conv2d<float><<<nblk((long long)B * 25 * 128), 256, 0, h->stream>>>(a0, h->enc[1].W, h->enc[1].b, a1, B, 5, 5, 64, 5, 5, 128, 3, 3, 1, 1, 1, 1);
     k_dense<<<nblk((long long)B * 128), 256, 0, h->stream>>>(a1, h->enc[2].W, h->enc[2].b, a2, B, 3200, 128, 1);
     k_dense<<<nblk((long long)B * 50), 256, 0, h->stream>>>(a2, h->enc[3].W, h->enc[3].b, z_dev, B, 128, 50, 0);
     h->launches += 4;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
 }
+template <int KD, int ND>
+int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* Wbf, const float* bias, __nv_bfloat16* out,
+                    int B, int H) {
+    const long long M = (long long)B * H * H;
+    const size_t smem = srtc::convT_tc_smem<KD, ND>();
+    static bool attr_done = false;
+    if (!attr_done) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<KD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    srtc::k_convT2x2_tc<KD, ND><<<(unsigned)((M + 127) / 128), 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
+    h->launches += 1;
+    SRCK(cudaGetLastError());
+    return SRCFD_OK;
+}
+// tensor-core ConvT layer l (1..4): input H = 25 * 2^(l-1), Cin = 128 >> (l-1)
+int run_convT_tc(srcfd_sr* h, int l, const __nv_bfloat16* in, __nv_bfloat16* out, int B) {
+    switch (l) {
+        case 1: return launch_convT_tc<128, 256>(h, in, h->dec[2].Wbf, h->dec[2].b, out, B, 25);
+        case 2: return launch_convT_tc<64, 128>(h, in, h->dec[3].Wbf, h->dec[3].b, out, B, 50);
+        case 3: return launch_convT_tc<32, 64>(h, in, h->dec[4].Wbf, h->dec[4].b, out, B, 100);
+        case 4: return launch_convT_tc<16, 32>(h, in, h->dec[5].Wbf, h->dec[5].b, out, B, 200);
+    }
+    return sr_fail(SRCFD_ERR_ARG, "bad tensor-core layer");
+}
+
 // decoder on `B` samples: z_dev (B,50) -> out_dev (B,400,400,1)
 int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
     k_dense<<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
     const int hw[6] = {12, 25, 50, 100, 200, 400}, ch[6] = {256, 128, 64, 32, 16, 8};
-    for (int l = 0; l < 5; ++l) {
-        const int k = (l == 0) ? 3 : 2;
-        k_conv2d_transpose<<<nblk((long long)B * hw[l + 1] * hw[l + 1] * ch[l + 1]), 256, 0, h->stream>>>(
-            h->act[l], h->dec[l + 1].W, h->dec[l + 1].b, h->act[l + 1], B, hw[l], hw[l], ch[l], hw[l + 1], hw[l + 1], ch[l + 1], k, 2, 1);
+    h->launches += 1;
+    if (h->precision == 0) {
+        for (int l = 0; l < 5; ++l) {
+            const int k = (l == 0) ? 3 : 2;
+            k_conv2d_transpose<<<nblk((long long)B * hw[l + 1] * hw[l + 1] * ch[l + 1]), 256, 0, h->stream>>>(
+                h->act[l], h->dec[l + 1].W, h->dec[l + 1].b, h->act[l + 1], B, hw[l], hw[l], ch[l], hw[l + 1], hw[l + 1], ch[l + 1], k, 2, 1);
+        }
+        k_conv2d<float><<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
+        h->launches += 6;
+    } else {
+        // ConvT1 (3x3, overlapping taps) stays on the CUDA cores; its output feeds the tensor-core chain in bf16
+        k_conv2d_transpose<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(
+            h->act[0], h->dec[1].W, h->dec[1].b, h->act[1], B, 12, 12, 256, 25, 25, 128, 3, 2, 1);
+        const long long n1 = (long long)B * 25 * 25 * 128;
+        srtc::k_f32_to_bf16<<<(unsigned)std::min<long long>((n1 + 255) / 256, 4096), 256, 0, h->stream>>>(h->act[1], h->actbf[1], n1);
+        h->launches += 2;
+        for (int l = 1; l <= 4; ++l)
+            if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
+        k_conv2d<__nv_bfloat16><<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->actbf[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
+        h->launches += 1;
     }
-    k_conv2d<<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
-    h->launches += 7;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
 }
@@ -192,7 +241,9 @@ int srcfd_sr_destroy(srcfd_sr* h) {
     cudaSetDevice(h->dev);
     cudaStreamSynchronize(h->stream);
     for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
-    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); }
+    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); }
+    for (int i = 1; i < 6; ++i) cudaFree(h->actbf[i]);
+    cudaFree(h->tc_err);
     for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
     cudaFree(h->zin); cudaFree(h->xin);
     cudaEventDestroy(h->ea); cudaEventDestroy(h->eb);
@@ -228,6 +279,13 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
         if (int rc = upload(&h->dec[l + 1].W, wt.data(), wt.size(), h->stream)) return rc;
         SRCK(cudaStreamSynchronize(h->stream));      // wt is a temporary
         if (int rc = upload(&h->dec[l + 1].b, biases[l + 1], cout[l], h->stream)) return rc;
+        if (l >= 1) {     // tensor-core operand: the Keras layout (ky,kx,co | ci) is already the K-major (N, K) matrix
+            const size_t n = (size_t)taps[l] * cout[l] * cin[l];
+            std::vector<__nv_bfloat16> wb(n);
+            for (size_t i = 0; i < n; ++i) wb[i] = __float2bfloat16(kernels[l + 1][i]);
+            if (!h->dec[l + 1].Wbf) SRCK(cudaMalloc(&h->dec[l + 1].Wbf, n * sizeof(__nv_bfloat16)));
+            SRCK(cudaMemcpy(h->dec[l + 1].Wbf, wb.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        }
     }
     if (int rc = upload(&h->dec[6].W, kernels[6], 3 * 3 * 8 * 1, h->stream)) return rc;
     if (int rc = upload(&h->dec[6].b, biases[6], 1, h->stream)) return rc;
@@ -295,6 +353,35 @@ int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev,
     float f = 0.f;
     SRCK(cudaEventElapsedTime(&f, h->ea, h->eb));
     if (ms) *ms = f;
+    return SRCFD_OK;
+}
+// 0 = fp32 CUDA cores (default, parity path); 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers
+int srcfd_sr_set_precision(srcfd_sr* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    h->precision = mode;
+    return SRCFD_OK;
+}
+// 1 if a tensor-core kernel ever timed out waiting for its accumulator (diagnostic; the kernels never hang)
+int srcfd_sr_tc_error(srcfd_sr* h, int* flag) {
+    if (!h || !flag) return sr_fail(SRCFD_ERR_ARG, "null argument");
+    *flag = 0;
+    if (h->tc_err) { SRCK(cudaSetDevice(h->dev)); SRCK(cudaMemcpy(flag, h->tc_err, sizeof(int), cudaMemcpyDeviceToHost)); }
+    return SRCFD_OK;
+}
+// One tensor-core ConvT layer in isolation (layer 1..4 = conv2d_transpose_1.._4): in (B,H,H,Cin) fp32 host ->
+// out (B,2H,2H,Cout) fp32 host, operands rounded to bf16 on the way in, bf16 result widened on the way out.
+int srcfd_sr_debug_convT_tc(srcfd_sr* h, int layer, const float* in, int B, float* out) {
+    if (!h || !in || !out || layer < 1 || layer > 4 || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_dec) return sr_fail(SRCFD_ERR_ARG, "decoder weights not set");
+    SRCK(cudaSetDevice(h->dev));
+    if (int rc = ensure_chunk(h, std::max(B, 1))) return rc;
+    const long long nin = (long long)B * DEC_ACT_ELEMS[layer], nout = (long long)B * DEC_ACT_ELEMS[layer + 1];
+    SRCK(cudaMemcpyAsync(h->act[layer], in, nin * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    srtc::k_f32_to_bf16<<<1024, 256, 0, h->stream>>>(h->act[layer], h->actbf[layer], nin);
+    if (int rc = run_convT_tc(h, layer, h->actbf[layer], h->actbf[layer + 1], B)) return rc;
+    srtc::k_bf16_to_f32<<<1024, 256, 0, h->stream>>>(h->actbf[layer + 1], h->act[layer + 1], nout);
+    SRCK(cudaMemcpyAsync(out, h->act[layer + 1], nout * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    SRCK(cudaStreamSynchronize(h->stream));
     return SRCFD_OK;
 }
 int srcfd_sr_launch_count(srcfd_sr* h, int64_t* n) {

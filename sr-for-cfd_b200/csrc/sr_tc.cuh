@@ -1,0 +1,160 @@
+// sr_tc.cuh -- tensor-core (tcgen05 / TMEM) path for the decoder's stride-2, 2x2 transposed convolutions.
+//
+// Conv2DTranspose(Cout, 2x2, stride 2, 'valid') has non-overlapping taps, so it IS a GEMM:
+//     D[m, n] = sum_ci A[m, ci] * Wk[n, ci]      m = (b, y, x) input pixel,  n = (dy, dx, co)
+//     out[b, 2y+dy, 2x+dx, co] = swish(D[m, n] + bias[co])
+// A is the NHWC activation itself (M x K, K = Cin contiguous => "K-major", no im2col: implicit GEMM); Wk is the
+// Keras kernel (kh, kw, Cout, Cin) read as (N = 4*Cout) x K, also K-major.  One CTA computes a 128 x N tile:
+//   * 128 threads stage the A tile and the whole weight matrix in shared memory in the canonical K-major
+//     SWIZZLE_NONE layout of the UMMA shared-memory descriptor: 8-row x 16-byte core matrices, 128 B each,
+//     consecutive 8-row groups SBO = 128 B apart, consecutive 16-byte K-chunks LBO = (rows/8)*128 B apart;
+//   * one thread issues K/16 tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128, N = 4*Cout) into a TMEM
+//     accumulator allocated by warp 0, then tcgen05.commit -> mbarrier;
+//   * each warp reads its 32 TMEM lanes with tcgen05.ld (32x32b.x16), adds the bias, applies swish and writes
+//     the pixel-shuffled bf16 output (for a fixed row and dy the (dx, co) run is contiguous in NHWC).
+// K = Cin <= 128 fits one stage, so there is no K pipeline inside a CTA; several CTAs per SM overlap instead.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srtc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);              // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading byte offset [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                                // descriptor version 1 (sm_100)
+    return d;                                              // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major (InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+
+// A: (M, KD) bf16 row-major.  Wk: (ND, KD) bf16 row-major (ND = 4*Cout, n = (dy*2+dx)*Cout + co).  bias: (Cout) fp32.
+// out: (B, 2H, 2W, Cout) bf16.  M = B*H*W.  err: set to 1 if the MMA completion wait times out (never hang).
+template <int KD, int ND>
+__global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Wk,
+                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                      long long M, int H, int Wd, int* err) {
+    constexpr int MT = 128, COUT = ND / 4;
+    constexpr uint32_t LBO_A = (MT / 8) * 128, LBO_B = (ND / 8) * 128, SBO = 128;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sA = smem_raw;                              // MT x KD bf16, canonical layout
+    unsigned char* sB = smem_raw + (size_t)MT * KD * 2;        // ND x KD bf16
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * MT;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ND < 32 ? 32 : ND) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- stage A (zero rows past M) and Wk: one 16-byte chunk = 8 bf16 of one row
+    constexpr int KC = KD / 8;
+    for (int c = tid; c < MT * KC; c += 128) {
+        const int r = c / KC, kc = c - r * KC;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (m0 + r < M) v = *reinterpret_cast<const uint4*>(A + (m0 + r) * KD + kc * 8);
+        *reinterpret_cast<uint4*>(sA + (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16) = v;
+    }
+    for (int c = tid; c < ND * KC; c += 128) {
+        const int n = c / KC, kc = c - n * KC;
+        const uint4 v = *reinterpret_cast<const uint4*>(Wk + (size_t)n * KD + kc * 8);
+        *reinterpret_cast<uint4*>(sB + (size_t)kc * LBO_B + (n >> 3) * SBO + (n & 7) * 16) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(MT, ND);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+        for (int k = 0; k < KD / 16; ++k) {                       // one MMA consumes K = 16 = two 16-byte chunks
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)k * 2 * LBO_A, LBO_A, SBO);
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)k * 2 * LBO_B, LBO_B, SBO);
+            umma_bf16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    // ---- wait for the accumulator (bounded: never hang the GPU)
+    {
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        }
+        if (!done && lane == 0) atomicExch(err, 1);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: thread = accumulator row (TMEM lane) 32*warp + lane
+    const long long m = m0 + warp * 32 + lane;
+    const bool valid = m < M;
+    long long pix = valid ? m : 0;
+    const int x = (int)(pix % Wd); pix /= Wd;
+    const int y = (int)(pix % H);
+    const long long b = pix / H;
+    const int OW = 2 * Wd;
+#pragma unroll 1
+    for (int c0 = 0; c0 < ND; c0 += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+            // columns c0..c0+15 : n = tap*COUT + co (COUT is a multiple of 8, so 8-column groups stay inside one tap)
+#pragma unroll
+            for (int g = 0; g < 16; g += 8) {
+                const int n = c0 + g, tap = n / COUT, co = n - tap * COUT;
+                const int dy = tap >> 1, dx = tap & 1;
+                __nv_bfloat16 o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16(swishf(__uint_as_float(v[g + e]) + bias[co + e]));
+                __nv_bfloat16* dst = out + ((((long long)b * (2 * H) + (2 * y + dy)) * OW + (2 * x + dx)) * COUT + co);
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(ND < 32 ? 32 : ND) : "memory");
+}
+
+template <int KD, int ND>
+constexpr size_t convT_tc_smem() { return (size_t)(128 + ND) * KD * 2; }
+
+// fp32 -> bf16 elementwise
+__global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        out[t] = __float2bfloat16(in[t]);
+}
+__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        out[t] = __bfloat162float(in[t]);
+}
+
+}  // namespace srtc

@@ -166,3 +166,24 @@ def launch_count(device=None) -> int:
     n = C.c_int64(0)
     _sr_check(capi.lib().srcfd_sr_launch_count(_context(device)["h"], C.byref(n)))
     return n.value
+
+
+def set_precision(mode: str = "fp32", device=None):
+    """'fp32' (default; CUDA cores, the parity path) or 'bf16' (tcgen05 tensor cores for the 2x2/stride-2 ConvT layers)."""
+    _sr_check(capi.lib().srcfd_sr_set_precision(_context(device)["h"], C.c_int({"fp32": 0, "bf16": 1}[mode])))
+
+
+def tc_error(device=None) -> bool:
+    f = C.c_int(0)
+    _sr_check(capi.lib().srcfd_sr_tc_error(_context(device)["h"], C.byref(f)))
+    return bool(f.value)
+
+
+def debug_convT_tc(decoder: Decoder, layer: int, x) -> np.ndarray:
+    """One tensor-core ConvT layer (1..4) in isolation: x (B,H,H,Cin) fp32 -> (B,2H,2H,Cout) fp32 (bf16 operands)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, H = x.shape[0], x.shape[1]
+    cout = DECODER_SHAPES[DECODER_LAYERS[layer + 1]][2]
+    out = np.empty((B, 2 * H, 2 * H, cout), dtype=np.float32)
+    _sr_check(capi.lib().srcfd_sr_debug_convT_tc(decoder._bind(), C.c_int(layer), x.ctypes.data_as(_fp), C.c_int(B), out.ctypes.data_as(_fp)))
+    return out

@@ -56,3 +56,43 @@ def test_super_resolution_workflow(golden_dir):
     ref = reshape_square_to_rectangular(ref, 400, 400, 10.0, 3.0)
     for c in "uvp":
         np.testing.assert_allclose(hr[c], ref[c], rtol=2e-4, atol=1e-4)
+
+
+def _bf16_round(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("layer", [1, 2, 3, 4])
+def test_tensor_core_convT_layer(layer):
+    """tcgen05 implicit-GEMM ConvT vs the CPU restatement with the SAME bf16-rounded operands: only the fp32
+    accumulation order and the final bf16 rounding of the output differ (tolerance: 1 bf16 ulp ~ 0.8 % relative)."""
+    from srcfd import sr
+    dec = sr.synthetic_decoder(0)
+    name = sr.DECODER_LAYERS[layer + 1]
+    cin = sr.DECODER_SHAPES[name][3]
+    H = 25 * 2 ** (layer - 1)
+    B = 2 if layer < 4 else 1
+    x = np.random.default_rng(layer).standard_normal((B, H, H, cin)).astype(np.float32)
+    got = sr.debug_convT_tc(dec, layer, x)
+    assert not sr.tc_error()
+    ref = S.swish(S.conv2d_transpose_valid(_bf16_round(x), _bf16_round(dec.weights[f"{name}/kernel"]), dec.weights[f"{name}/bias"], 2))
+    np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2)
+    assert np.abs(got - ref).max() < 0.02 and np.abs(ref).max() > 0.1
+
+
+def test_decoder_bf16_tensor_core_path():
+    """Whole decoder with the tensor-core layers: bf16 operands => compare with the fp32 restatement at 3e-2 of the
+    output range (this path is the throughput option; fp32 stays the default and the parity path)."""
+    from srcfd import sr
+    dec = sr.synthetic_decoder(0)
+    z = np.random.default_rng(11).standard_normal((3, 50)).astype(np.float32)
+    sr.set_precision("bf16")
+    try:
+        out = dec.predict(z)
+    finally:
+        sr.set_precision("fp32")
+    assert not sr.tc_error()
+    ref = S.decoder_forward(z, dec.weights)
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() <= 3e-2 * scale, (np.abs(out - ref).max(), scale)
