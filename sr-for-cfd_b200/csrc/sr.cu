@@ -27,8 +27,14 @@ int sr_fail(int code, const std::string& m) { g_sr_err = m; return code; }
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
 
 // out[b, n] = act(in[b, :] . W[:, n] + bias[n]);  W is (K, N) row-major (Keras Dense layout)
+template <typename TOUT>
+__device__ __forceinline__ void st_act(TOUT* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TOUT>
 __global__ void k_dense(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
-                        float* __restrict__ out, int B, int K, int N, int act) {
+                        TOUT* __restrict__ out, int B, int K, int N, int act) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)B * N) return;
     const int n = (int)(t % N), b = (int)(t / N);
@@ -36,7 +42,7 @@ __global__ void k_dense(const float* __restrict__ in, const float* __restrict__ 
     float acc = 0.f;
     for (int k = 0; k < K; ++k) acc = fmaf(x[k], W[(long long)k * N + n], acc);
     acc += bias[n];
-    out[t] = act ? swishf(acc) : acc;
+    st_act<TOUT>(out + t, act ? swishf(acc) : acc);
 }
 
 // Conv2D, cross-correlation, zero padding (pt, pl) at the top/left; W (kh, kw, Cin, Cout)
@@ -143,7 +149,7 @@ int ensure_chunk(srcfd_sr* h, int chunk) {
     SRCK(cudaMalloc(&h->act[7], (size_t)chunk * 3200 * sizeof(float)));   // encoder scratch (5*5*128)
     SRCK(cudaMalloc(&h->zin, (size_t)chunk * 192 * sizeof(float)));   // (chunk,128) dense scratch + (chunk,50) latents
     SRCK(cudaMalloc(&h->xin, (size_t)chunk * 1600 * sizeof(float)));
-    for (int i = 1; i < 6; ++i) { cudaFree(h->actbf[i]); SRCK(cudaMalloc(&h->actbf[i], (size_t)chunk * DEC_ACT_ELEMS[i] * sizeof(__nv_bfloat16))); }
+    for (int i = 0; i < 6; ++i) { cudaFree(h->actbf[i]); SRCK(cudaMalloc(&h->actbf[i], (size_t)chunk * DEC_ACT_ELEMS[i] * sizeof(__nv_bfloat16))); }
     if (!h->tc_err) { SRCK(cudaMalloc(&h->tc_err, sizeof(int))); SRCK(cudaMemset(h->tc_err, 0, sizeof(int))); }
     h->chunk = chunk;
     return SRCFD_OK;
@@ -157,8 +163,8 @@ int run_encoder(srcfd_sr* h, const float* x_dev, int B, float* z_dev) {
     float* a2 = h->zin;          // (B,128)
     k_conv2d<float><<<nblk((long long)B * 25 * 64), 256, 0, h->stream>>>(x_dev, h->enc[0].W, h->enc[0].b, a0, B, 10, 10, 1, 5, 5, 64, 3, 3, 2, 0, 0, 1);
     k_conv2d<float><<<nblk((long long)B * 25 * 128), 256, 0, h->stream>>>(a0, h->enc[1].W, h->enc[1].b, a1, B, 5, 5, 64, 5, 5, 128, 3, 3, 1, 1, 1, 1);
-    k_dense<<<nblk((long long)B * 128), 256, 0, h->stream>>>(a1, h->enc[2].W, h->enc[2].b, a2, B, 3200, 128, 1);
-    k_dense<<<nblk((long long)B * 50), 256, 0, h->stream>>>(a2, h->enc[3].W, h->enc[3].b, z_dev, B, 128, 50, 0);
+    k_dense<float><<<nblk((long long)B * 128), 256, 0, h->stream>>>(a1, h->enc[2].W, h->enc[2].b, a2, B, 3200, 128, 1);
+    k_dense<float><<<nblk((long long)B * 50), 256, 0, h->stream>>>(a2, h->enc[3].W, h->enc[3].b, z_dev, B, 128, 50, 0);
     h->launches += 4;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
@@ -188,7 +194,10 @@ int run_convT_tc(srcfd_sr* h, int l, const __nv_bfloat16* in, __nv_bfloat16* out
 
 // decoder on `B` samples: z_dev (B,50) -> out_dev (B,400,400,1)
 int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
-    k_dense<<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
+    if (h->precision == 0)
+        k_dense<float><<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
+    else
+        k_dense<__nv_bfloat16><<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->actbf[0], B, 50, 36864, 1);
     const int hw[6] = {12, 25, 50, 100, 200, 400}, ch[6] = {256, 128, 64, 32, 16, 8};
     h->launches += 1;
     if (h->precision == 0) {
@@ -200,11 +209,17 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         k_conv2d<float><<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
         h->launches += 6;
     } else {
-        // ConvT1 (3x3, overlapping taps) stays on the CUDA cores; its output feeds the tensor-core chain in bf16
-        k_conv2d_transpose<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(
-            h->act[0], h->dec[1].W, h->dec[1].b, h->act[1], B, 12, 12, 256, 25, 25, 128, 3, 2, 1);
-        const long long n1 = (long long)B * 25 * 25 * 128;
-        srtc::k_f32_to_bf16<<<(unsigned)std::min<long long>((n1 + 255) / 256, 4096), 256, 0, h->stream>>>(h->act[1], h->actbf[1], n1);
+        // ConvT1 (3x3, stride 2: overlapping taps): tensor-core GEMM per tap into Y (act[5] reused as fp32 scratch,
+        // B*144 x 1152), then col2im + bias + swish -> bf16 activation
+        {
+            const long long M = (long long)B * 144;
+            const size_t smem = srtc::convT_tc_smem<256, 128>();
+            static bool attr_done = false;
+            if (!attr_done) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<256, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+            srtc::k_convT2x2_tc<256, 128, 1><<<dim3((unsigned)((M + 127) / 128), 9), 128, smem, h->stream>>>(
+                h->actbf[0], h->dec[1].Wbf, h->dec[1].b, nullptr, M, 12, 12, h->tc_err, h->act[5], 1152);
+            srtc::k_col2im_3x3s2<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->actbf[1], B);
+        }
         h->launches += 2;
         for (int l = 1; l <= 4; ++l)
             if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
@@ -242,7 +257,7 @@ int srcfd_sr_destroy(srcfd_sr* h) {
     cudaStreamSynchronize(h->stream);
     for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
     for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); }
-    for (int i = 1; i < 6; ++i) cudaFree(h->actbf[i]);
+    for (int i = 0; i < 6; ++i) cudaFree(h->actbf[i]);
     cudaFree(h->tc_err);
     for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
     cudaFree(h->zin); cudaFree(h->xin);
@@ -279,7 +294,7 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
         if (int rc = upload(&h->dec[l + 1].W, wt.data(), wt.size(), h->stream)) return rc;
         SRCK(cudaStreamSynchronize(h->stream));      // wt is a temporary
         if (int rc = upload(&h->dec[l + 1].b, biases[l + 1], cout[l], h->stream)) return rc;
-        if (l >= 1) {     // tensor-core operand: the Keras layout (ky,kx,co | ci) is already the K-major (N, K) matrix
+        {                 // tensor-core operand: the Keras layout (ky,kx,co | ci) is already the K-major (N, K) matrix
             const size_t n = (size_t)taps[l] * cout[l] * cin[l];
             std::vector<__nv_bfloat16> wb(n);
             for (size_t i = 0; i < n; ++i) wb[i] = __float2bfloat16(kernels[l + 1][i]);

@@ -44,11 +44,16 @@ __device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)
 
 // A: (M, KD) bf16 row-major.  Wk: (ND, KD) bf16 row-major (ND = 4*Cout, n = (dy*2+dx)*Cout + co).  bias: (Cout) fp32.
 // out: (B, 2H, 2W, Cout) bf16.  M = B*H*W.  err: set to 1 if the MMA completion wait times out (never hang).
-template <int KD, int ND>
+// EPI = 0: the fused bias + swish + pixel-shuffle epilogue described above (out = bf16 NHWC activation).
+// EPI = 1: plain GEMM tile, fp32 D stored to Y[m * ldy + blockIdx.y * ND + n]; Wk is offset by blockIdx.y * ND rows.
+//          Used for the 3x3/stride-2 ConvT (overlapping taps): Y holds the 9 per-tap products, k_col2im_3x3s2 sums them.
+template <int KD, int ND, int EPI = 0>
 __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Wk,
                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                      long long M, int H, int Wd, int* err) {
+                                                      long long M, int H, int Wd, int* err, float* __restrict__ Y = nullptr,
+                                                      int ldy = 0) {
     constexpr int MT = 128, COUT = ND / 4;
+    if (EPI == 1) Wk += (size_t)blockIdx.y * ND * KD;
     constexpr uint32_t LBO_A = (MT / 8) * 128, LBO_B = (ND / 8) * 128, SBO = 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sA = smem_raw;                              // MT x KD bf16, canonical layout
@@ -124,7 +129,14 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
+        if (EPI == 1) {
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(Y + m * ldy + (long long)blockIdx.y * ND + c0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            }
+        } else if (valid) {
             // columns c0..c0+15 : n = tap*COUT + co (COUT is a multiple of 8, so 8-column groups stay inside one tap)
 #pragma unroll
             for (int g = 0; g < 16; g += 8) {
@@ -146,6 +158,29 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
 
 template <int KD, int ND>
 constexpr size_t convT_tc_smem() { return (size_t)(128 + ND) * KD * 2; }
+
+// Conv2DTranspose(128, 3x3, stride 2, valid) from the per-tap products Y (B*144, 9*128): sum the <= 4 taps that hit
+// each output pixel, add bias, swish, write the bf16 NHWC activation (B, 25, 25, 128).
+__global__ void k_col2im_3x3s2(const float* __restrict__ Y, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * 25 * 25 * 128) return;
+    const int co = (int)(t & 127);
+    long long p = t >> 7;
+    const int X = (int)(p % 25); p /= 25;
+    const int Yo = (int)(p % 25);
+    const long long b = p / 25;
+    float acc = bias[co];
+    for (int ky = Yo & 1; ky < 3; ky += 2) {
+        const int y = (Yo - ky) >> 1;
+        if (y < 0 || y >= 12) continue;
+        for (int kx = X & 1; kx < 3; kx += 2) {
+            const int x = (X - kx) >> 1;
+            if (x < 0 || x >= 12) continue;
+            acc += Y[((b * 12 + y) * 12 + x) * 1152 + (ky * 3 + kx) * 128 + co];
+        }
+    }
+    out[t] = __float2bfloat16(swishf(acc));
+}
 
 // fp32 -> bf16 elementwise
 __global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
