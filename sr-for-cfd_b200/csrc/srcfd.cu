@@ -63,6 +63,11 @@ struct srcfd_handle {
     Gs2Plan plan2[3];
     int grid_gs2[3] = {0, 0, 0};
     double* halo = nullptr;
+    // second problem of a paired (u,v) momentum launch
+    double *scratch2 = nullptr, *partials2 = nullptr, *halo2 = nullptr;
+    int* prog2 = nullptr;
+    bool pair_momentum = true;   // SRCFD_PAIR=0 disables
+    bool ghosts_fresh = false;   // v ghost column known to equal -v(1,j): set by the BC passes, cleared by uploads
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
@@ -225,6 +230,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
+    cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -271,8 +277,15 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
         CKB(cudaMalloc(&h->trace, sizeof(long long) * h->trace_n));
         CKB(cudaMemsetAsync(h->trace, 0, sizeof(long long) * h->trace_n, h->stream));
     }
-    CKB(cudaMalloc(&h->halo, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64));
-    CKB(cudaMemsetAsync(h->halo, 0, sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64, h->stream));
+    const size_t halo_bytes = sizeof(double) * (size_t)2 * WF2_KMAX * maxbands * 2 * h->K.pitch + 64;
+    CKB(cudaMalloc(&h->halo, halo_bytes));
+    CKB(cudaMemsetAsync(h->halo, 0, halo_bytes, h->stream));
+    CKB(cudaMalloc(&h->halo2, halo_bytes));
+    CKB(cudaMemsetAsync(h->halo2, 0, halo_bytes, h->stream));
+    CKB(cudaMalloc(&h->scratch2, sizeof(double) * (P + pad)));
+    CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
+    CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
+    if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
     CKB(cudaMalloc(&h->partials, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     CKB(cudaMalloc(&h->res_partials, sizeof(double) * 3 * (size_t)(h->tail_blocks + 1)));
@@ -302,7 +315,9 @@ int srcfd_set_params(srcfd_handle* h, const srcfd_params* params) {
     if (params->inner_max > h->inner_cap) return fail(SRCFD_ERR_ARG, "inner_max cannot exceed its value at creation");
     const int keep_ctas = h->p.max_ctas;
     h->p = *params; h->p.max_ctas = keep_ctas;
-    h->K = make_consts(*params); h->bc = make_bc(*params);
+    const BcSpec nb = make_bc(*params);
+    if (memcmp(&nb, &h->bc, sizeof(BcSpec)) != 0) h->ghosts_fresh = false;   // new BCs: ghosts no longer known consistent
+    h->K = make_consts(*params); h->bc = nb;
     return SRCFD_OK;
 }
 
@@ -317,7 +332,7 @@ int srcfd_stream(srcfd_handle* h, uint64_t* stream) {
 int srcfd_upload(srcfd_handle* h, const double* Var, const double* VarOld, const double* Ff, const double* residual) {
     CKH(h);
     const size_t P = (size_t)h->K.plane;
-    if (Var) CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
+    if (Var) { CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream)); h->ghosts_fresh = false; }
     if (VarOld) CK(cudaMemcpyAsync(h->VarOld, VarOld, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
     if (Ff) CK(cudaMemcpyAsync(h->Ff, Ff, sizeof(double) * 4 * P, cudaMemcpyHostToDevice, h->stream));
     if (residual) CK(cudaMemcpyAsync((char*)h->ctrl + offsetof(Ctrl, residual), residual, sizeof(double) * 3, cudaMemcpyHostToDevice, h->stream));
@@ -428,7 +443,7 @@ static int ev_drain(srcfd_handle* h) {
 }
 
 // One inner solve: op in {OP_PRESSURE, OP_UPWIND, OP_QUICK} on plane k, counters in slot.
-static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
+static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = false) {
     SolveArgs a;
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
@@ -442,7 +457,10 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
         ga.trace = h->trace;
-        ga.halo = h->halo; ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp; ga.K = P.K;
+        ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp; ga.K = P.K;
+        ga.np = pair ? 2 : 1;
+        ga.pr[0] = Gs2Prob{k, slot, h->scratch, h->partials, h->prog, h->halo};
+        ga.pr[1] = Gs2Prob{1, 1, h->scratch2, h->partials2, h->prog2, h->halo2};   // pair: k = slot = 0 above, 1 here
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
@@ -463,10 +481,23 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot) {
 static int l_implicit_solve(srcfd_handle* h) {
     TRY(l_zero_residual(h));
     const int mop = h->p.scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND;
-    for (int k = 0; k < 2; ++k) {
-        TRY(l_inner_solve(h, mop, k, k));
-        if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));
-        TRY(l_apply_bc(h, k));
+    // The u and v momentum solves are independent (different planes, same read-only Ff): one paired wavefront
+    // launch when the reference order is in use.  The BFS inlet pass for k = 0 also rewrites the v ghost column
+    // (BFS.py:562) from the current v; that is a no-op exactly when the ghosts are fresh, so pair only then.
+    const bool pair = h->pair_momentum && h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 &&
+                      (!h->bc.bfs || h->ghosts_fresh);
+    if (pair) {
+        TRY(l_inner_solve(h, mop, 0, 0, true));
+        for (int k = 0; k < 2; ++k) {
+            if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));
+            TRY(l_apply_bc(h, k));
+        }
+    } else {
+        for (int k = 0; k < 2; ++k) {
+            TRY(l_inner_solve(h, mop, k, k));
+            if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));
+            TRY(l_apply_bc(h, k));
+        }
     }
     TRY(l_linear_interpolation(h, true));
     TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
@@ -476,6 +507,7 @@ static int l_implicit_solve(srcfd_handle* h) {
     TRY(l_apply_bc(h, 0));
     TRY(l_apply_bc(h, 1));
     TRY(l_update_flux(h));
+    h->ghosts_fresh = true;
     return SRCFD_OK;
 }
 
@@ -508,6 +540,7 @@ int srcfd_initialize_fields(srcfd_handle* h, int zero_first) {
     for (int k = 0; k < 3; ++k) TRY(l_apply_bc(h, k));
     TRY(l_copy_new_to_old(h));
     TRY(l_linear_interpolation(h, false));
+    h->ghosts_fresh = true;
     return SRCFD_OK;
 }
 
@@ -610,16 +643,19 @@ int srcfd_solve(srcfd_handle* h, int64_t max_iterations, const double crit[3], i
 int srcfd_k_copy_new_to_old(srcfd_handle* h) { CKH(h); return l_copy_new_to_old(h); }
 int srcfd_k_apply_bc(srcfd_handle* h, int k) {
     CKH(h);
+    h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k);
 }
 int srcfd_k_apply_bc_configured(srcfd_handle* h, int k) {
     CKH(h);
+    h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k, 1);
 }
 int srcfd_k_apply_bfs_inlet(srcfd_handle* h, int k) {
     CKH(h);
+    h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k, 2);
 }
@@ -627,11 +663,13 @@ int srcfd_k_linear_interpolation(srcfd_handle* h) { CKH(h); return l_linear_inte
 int srcfd_k_update_flux(srcfd_handle* h) { CKH(h); return l_update_flux(h); }
 int srcfd_k_under_relax(srcfd_handle* h, int k, double alpha) {
     CKH(h);
+    h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_under_relax(h, k, alpha);
 }
 int srcfd_k_correct_velocity(srcfd_handle* h, double residual_out[3]) {
     CKH(h);
+    h->ghosts_fresh = false;
     TRY(l_correct_velocity(h));
     if (residual_out) return srcfd_download(h, nullptr, nullptr, nullptr, residual_out);
     return SRCFD_OK;
@@ -651,6 +689,7 @@ int srcfd_k_solve_pressure(srcfd_handle* h, int32_t* sweeps, double* last_rms) {
 }
 int srcfd_k_solve_momentum(srcfd_handle* h, int k, int scheme, int32_t* sweeps, double* last_rms) {
     CKH(h);
+    h->ghosts_fresh = false;
     if (k < 0 || k > 1) return fail(SRCFD_ERR_ARG, "momentum is solved for k = 0 (u) or 1 (v)");
     if (scheme != SRCFD_SCHEME_UPWIND && scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
     TRY(l_inner_solve(h, scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND, k, k));
