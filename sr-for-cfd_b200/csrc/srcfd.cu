@@ -14,6 +14,7 @@
 #include "tail_kernels.cuh"
 #include "inner_solvers.cuh"
 #include "inner_gs2.cuh"
+#include "inner_gs3.cuh"
 
 using namespace srcfd;
 
@@ -68,6 +69,14 @@ struct srcfd_handle {
     int* prog2 = nullptr;
     bool pair_momentum = true;   // SRCFD_PAIR=0 disables
     bool ghosts_fresh = false;   // v ghost column known to equal -v(1,j): set by the BC passes, cleared by uploads
+    // third-generation pressure solve (inner_gs3.cuh): full-height groups, diagonal streams
+    bool gs3 = false;            // usable for this grid (SRCFD_GS3=0 disables)
+    int gs3_K = 4, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 8, gs3_grid = 0;
+    size_t gs3_smem = 0;
+    const void* gs3_fn = nullptr;
+    uint4* gs3_ll = nullptr;
+    double* gs3_rhsS = nullptr;
+    unsigned long long* gs3_epoch = nullptr;
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
@@ -182,7 +191,35 @@ static int plan_gs2(srcfd_handle* h, int op) {
     return fail(SRCFD_ERR_ARG, "cannot band the grid for the wavefront kernel");
 }
 
+// The full-height pressure kernel needs one thread per row (+2 ghost rows) in a single CTA and tags with room for
+// every boundary of a run; other grids keep the banded K-sweep kernel.
+static int plan_gs3(srcfd_handle* h) {
+    h->gs3 = false;
+    if (const char* e = getenv("SRCFD_GS3")) if (atoi(e) == 0) return SRCFD_OK;
+    const int nx = h->p.nx, ny = h->p.ny;
+    const int RP = ((nx + 31) / 32) * 32 + 32;          // threads: one per row, plus the ghost warp
+    if (RP > WF3_MAXT || h->inner_cap + 2 >= 4096) return SRCFD_OK;
+    if (const char* e = getenv("SRCFD_K3")) h->gs3_K = std::max(1, std::min(WF3_KMAX, atoi(e)));
+    if (const char* e = getenv("SRCFD_NBUF")) h->gs3_nbuf = std::max(2, atoi(e));
+    h->gs3_RP = RP; h->gs3_ND = nx + ny + 2;
+    const size_t per = sizeof(uint4) * (size_t)h->gs3_ND * WF3_RP;
+    while (h->gs3_nbuf > 2 && per * h->gs3_nbuf > ((size_t)1 << 31)) --h->gs3_nbuf;
+    if (per * h->gs3_nbuf > ((size_t)1 << 31)) return SRCFD_OK;
+    h->gs3_smem = sizeof(double) * ((size_t)3 * (WF3_KMAX + 1) * WF3_RP + 2 * (size_t)(ny + 2) + WF3_KMAX * 32);
+    if (h->gs3_smem > 200 * 1024) return SRCFD_OK;
+    h->gs3_fn = RP <= 448 ? (const void*)k_solve_gs3<448> : (const void*)k_solve_gs3<512>;   // 448 threads: 144 registers each
+    CK(cudaFuncSetAttribute(h->gs3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gs3_smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->gs3_fn, RP, h->gs3_smem));
+    if (occ < 1) return SRCFD_OK;
+    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+    h->gs3_grid = std::max(1, std::min(cap, h->num_sms));       // one group per SM at a time
+    h->gs3 = true;
+    return SRCFD_OK;
+}
+
 static int plan_launches(srcfd_handle* h) {
+    if (int rc = plan_gs3(h)) return rc;
     for (int op = 0; op < 3; ++op) if (int rc = plan_gs2(h, op)) return rc;
     const int nx = h->p.nx;
     h->nbands = (nx + WF_MAX_BAND - 1) / WF_MAX_BAND;
@@ -230,6 +267,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
+    cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -286,6 +324,18 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
+    if (h->gs3) {
+        const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
+        CKB(cudaMalloc(&h->gs3_ll, llb));
+        CKB(cudaMemsetAsync(h->gs3_ll, 0, llb, h->stream));
+        const size_t rb = sizeof(double) * (size_t)(WF3_PAD_LO + h->gs3_ND + WF3_PAD_HI) * WF3_RP;
+        CKB(cudaMalloc(&h->gs3_rhsS, rb));
+        CKB(cudaMemsetAsync(h->gs3_rhsS, 0, rb, h->stream));
+        CKB(cudaMalloc(&h->gs3_epoch, sizeof(unsigned long long)));
+        const unsigned long long one = 1;
+        CKB(cudaMemcpyAsync(h->gs3_epoch, &one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
+        CKB(cudaStreamSynchronize(h->stream));
+    }
     CKB(cudaMalloc(&h->partials, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     CKB(cudaMalloc(&h->res_partials, sizeof(double) * 3 * (size_t)(h->tail_blocks + 1)));
@@ -452,7 +502,13 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     void* args[] = {&a};
     EvPair ev;
     if (h->timing) if (int rc = ev_begin(h, op == OP_PRESSURE ? 0 : 1, ev)) return rc;
-    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
+    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
+        Gs3Args g3;
+        g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
+        g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * WF3_RP; g3.partials = h->partials; g3.epoch = h->gs3_epoch;
+        void* args3[] = {&g3};
+        CK(cudaLaunchCooperativeKernel(h->gs3_fn, dim3(h->gs3_grid), dim3(h->gs3_RP), args3, h->gs3_smem, h->stream));
+    } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
         const Gs2Plan& P = h->plan2[op];
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
