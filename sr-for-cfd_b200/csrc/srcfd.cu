@@ -71,7 +71,7 @@ struct srcfd_handle {
     bool ghosts_fresh = false;   // v ghost column known to equal -v(1,j): set by the BC passes, cleared by uploads
     // third-generation pressure solve (inner_gs3.cuh): full-height groups, diagonal streams
     bool gs3 = false;            // usable for this grid (SRCFD_GS3=0 disables)
-    int gs3_K = 4, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 8, gs3_grid = 0;
+    int gs3_K = 3, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 8, gs3_grid = 0;
     size_t gs3_smem = 0;
     const void* gs3_fn = nullptr;
     uint4* gs3_ll = nullptr;
@@ -311,7 +311,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     for (int op = 0; op < 3; ++op) { maxbands = std::max(maxbands, h->plan2[op].nbands); gmax = std::max(gmax, h->grid_gs2[op]); }
     h->n_partials = std::max((size_t)h->inner_cap * maxbands, (size_t)2 * gmax) + 64;
     if (getenv("SRCFD_TRACE")) {
-        h->trace_n = (size_t)(h->inner_cap / 4 + 2) * maxbands * 8;
+        h->trace_n = std::max((size_t)(h->inner_cap / 4 + 2) * maxbands * 8, (size_t)8 * 1024 + 64);
         CKB(cudaMalloc(&h->trace, sizeof(long long) * h->trace_n));
         CKB(cudaMemsetAsync(h->trace, 0, sizeof(long long) * h->trace_n, h->stream));
     }
@@ -505,7 +505,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
         Gs3Args g3;
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
-        g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * WF3_RP; g3.partials = h->partials; g3.epoch = h->gs3_epoch;
+        g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * WF3_RP; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
         void* args3[] = {&g3};
         CK(cudaLaunchCooperativeKernel(h->gs3_fn, dim3(h->gs3_grid), dim3(h->gs3_RP), args3, h->gs3_smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {

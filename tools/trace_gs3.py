@@ -1,0 +1,34 @@
+"""SRCFD_TRACE=1 python tools/trace_gs3.py [n] [sweeps]: per-group timeline of one full-height pressure solve."""
+import sys, os, ctypes as C
+os.environ["SRCFD_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sr-for-cfd_b200"))
+import numpy as np
+from srcfd import _capi as capi
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+K = int(os.environ.get("SRCFD_K3", "4"))
+p = capi.Params(); p.nx = p.ny = n; p.dx = p.dy = 1.0 / n; p.volp = p.dx * p.dy; p.dt = 1e-3; p.nu = 1e-2; p.rho = 1.0
+p.inner_tol = 0.0; p.inner_max = sweeps
+for k in range(3):
+    for s in range(4): p.bc_types[k][s] = 1 if k == 2 else 0
+h = capi.Handle(p)
+rng = np.random.default_rng(0); Var = rng.uniform(-1, 1, (3, n + 2, n + 2)); Ff = 1e-3 * rng.uniform(-1, 1, (4, n + 2, n + 2))
+for _ in range(3): h.upload(Var, Var, Ff); h.k_solve_pressure()
+buf = np.zeros(8 * 1024 + 64, dtype=np.int64)
+capi.lib().srcfd_trace_read(h._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int64(buf.size))
+G = (sweeps + K - 1) // K
+tr = buf[: 8 * G].reshape(G, 8); kt = buf[8 * 1024: 8 * 1024 + 4]
+t0 = kt[0]
+start, mid, end = [(tr[:, i] - t0) / 1e3 for i in range(3)]
+polls = tr[:, 4] - tr[:, 3]
+print(f"K={K} groups={G}: kernel prologue (rhs re-lay + grid sync) {(kt[1]-kt[0])/1e3:.1f} us, run end {(kt[2]-kt[0])/1e3:.1f} us, writeback end {(kt[3]-kt[0])/1e3:.1f} us")
+print(f"group duration: mean {(end-start).mean():.1f} us (first {end[0]-start[0]:.1f}); steps {2*n+2*K+1} -> {(end-start).mean()/(2*n+2*K+1)*1e3:.0f} ns/step avg")
+print(f"second half (mid..end): {((end-mid).mean()):.1f} us for {n+2*K+1} steps -> {(end-mid).mean()/(n+2*K+1)*1e3:.0f} ns/step")
+if G > 1:
+    lag_mid = np.diff(mid); lag_end = np.diff(end)
+    print(f"group-to-group lag at mid: mean {lag_mid.mean():.2f} us (min {lag_mid.min():.2f} max {lag_mid.max():.2f}); at end: mean {lag_end.mean():.2f}")
+    print(f"polls per group (all threads): mean {polls.mean():.0f}, first groups {polls[:6]}")
+    print("start of groups 0..5:", np.round(start[:6], 1), " ends:", np.round(end[:6], 1))
+    c = min(148, G - 1)
+    print(f"group {c}: start {start[c]:.1f} (group {c-148 if c>=148 else 0} ended {end[max(c-148,0)]:.1f})")
