@@ -90,6 +90,54 @@ def test_inner_solves_bit_exact(K, Nx, Ny, oname, ocode):
         assert n == m and np.array_equal(A, B), ("quick", k, n, m, np.max(np.abs(A - B)))
 
 
+@pytest.mark.parametrize("env", [{"SRCFD_GS3": "0"}, {"SRCFD_K3": "1"}, {"SRCFD_K3": "2"}, {"SRCFD_K3": "3"}, {"SRCFD_K3": "4"},
+                                 {"SRCFD_K3": "4", "SRCFD_NBUF": "2"}, {"SRCFD_SKIP_IDLE": "0"}])
+def test_pressure_kernel_generations_bit_exact(K, env, monkeypatch):
+    """Both reference-order pressure kernels (banded K-sweep groups; full-height groups with diagonal streams), every
+    group size, the smallest boundary ring, sweep counts that are and are not multiples of the group size, and the
+    speculative-run rerun when the tolerance is met early: all bit-exact against the oracle."""
+    from srcfd import kernels
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    for h in kernels._cache.values():
+        h.close()
+    kernels._cache.clear()                                  # the knobs are read when a handle is created
+    try:
+        for (Nx, Ny), caps in (((64, 48), (1, 7, 60)), ((33, 130), (5, 61)), ((400, 37), (13,)), ((480, 9), (10,)), ((1, 1), (3,)),
+                               ((2, 3), (9,))):
+            Var, VarOld, Ff = rnd_state(11 + Nx + Ny, Nx, Ny)
+            dx, dy = 1.3 / Nx, 0.9 / Ny
+            volp, dt, rho = dx * dy, 2e-3, 1.0
+            for cap in caps:
+                A, B = Var.copy(), Var.copy()
+                n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, dt, rho, volp, max_iter=cap)
+                m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, dt, rho, volp, max_iter=cap)
+                assert n == m and np.array_equal(A, B), (env, Nx, Ny, cap, n, m, np.max(np.abs(A - B)))
+        # early convergence: guesses alternately too large / too small exercise the rerun path
+        Nx, Ny = 40, 30
+        Var, VarOld, Ff = rnd_state(5, Nx, Ny, ff_scale=1e-4)
+        Var[2] *= 1e-3
+        dx, dy = 1.0 / Nx, 1.0 / Ny
+        counts = []
+        for tol in (1e-2, 1e-6, 1e-3, 1e-7, 1e-4):
+            A, B = Var.copy(), Var.copy()
+            n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, tolerance=tol, max_iter=500)
+            m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, tolerance=tol, max_iter=500)
+            assert n == m and np.array_equal(A, B), (env, tol, n, m)
+            counts.append(n)
+        assert len(set(counts)) >= 3, counts
+        # zero field: the reciprocal fast path is out of range for 0/b and the IEEE path must give the same bits
+        Z = np.zeros_like(Var); Fz = Ff.copy()
+        A, B = Z.copy(), Z.copy()
+        n = K.solve_pressure(A, Fz, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, max_iter=6)
+        m = O.solve_pressure(B, Fz, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, max_iter=6)
+        assert n == m and np.array_equal(A, B)
+    finally:
+        for h in kernels._cache.values():
+            h.close()
+        kernels._cache.clear()
+
+
 def test_break_semantics_and_rollback(K):
     """Exact 'stop after the first sweep with rms < tol' behaviour, including the speculative-group
     rollback of the wavefront order (the cached handle carries the previous call's sweep count as its guess)."""
