@@ -77,6 +77,11 @@ int srcfd_upload(srcfd_handle *h, const double *Var, const double *VarOld, const
 int srcfd_download(srcfd_handle *h, double *Var, double *VarOld, double *Ff, double *residual);
 /* Device addresses of the state arrays, for callers that keep inputs resident in HBM. */
 int srcfd_device_ptrs(srcfd_handle *h, uint64_t *Var, uint64_t *VarOld, uint64_t *Ff);
+/* Page-locked host memory for the arrays handed to srcfd_upload / srcfd_download (the reference keeps Var, VarOld, Ff
+ * as numpy arrays, PyCFD_ML_accelerated.py:340-345; allocating them here lets the copies run at full PCIe rate).
+ * Any host pointer is accepted by upload/download; pageable memory is simply slower. */
+int srcfd_host_alloc(uint64_t bytes, void **out);
+int srcfd_host_free(void *p);
 
 /* ---- composed path ------------------------------------------------------------------------- */
 /* _initialize_fields (LDC.py:377-389): optional zero fill, BC on u,v,p, copy_new_to_old, linear_interpolation. */
@@ -118,6 +123,10 @@ int srcfd_k_implicit_solve(srcfd_handle *h);
 int srcfd_timer_start(srcfd_handle *h);
 int srcfd_timer_stop(srcfd_handle *h, double *ms);
 /* Number of kernels this library has launched on the handle's stream since creation. */
+/* SRCFD_TRACE=1 only: raw per-task timestamps (ns) of the last wavefront launch; tools/trace_gs2.py, tools/trace_gs3.py. */
+int srcfd_trace_read(srcfd_handle *h, long long *out, int64_t n);
+/* Debug builds: raw doubles stored behind the scratch plane. */
+int srcfd_debug_read(srcfd_handle *h, double *out, int64_t n);
 int srcfd_launch_count(srcfd_handle *h, int64_t *launches);
 /* Device time (ms) and launches of the inner-solve kernels accumulated while timing is enabled
  * (CUDA events recorded around every inner-solve launch on the handle's stream). */

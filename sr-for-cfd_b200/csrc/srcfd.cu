@@ -66,12 +66,13 @@ struct srcfd_handle {
     double* halo = nullptr;
     // second problem of a paired (u,v) momentum launch
     double *scratch2 = nullptr, *partials2 = nullptr, *halo2 = nullptr;
+    double *sweeps1 = nullptr, *sweeps2 = nullptr;   // per-sweep result planes of a run's last group (two problems)
     int* prog2 = nullptr;
     bool pair_momentum = true;   // SRCFD_PAIR=0 disables
     bool ghosts_fresh = false;   // v ghost column known to equal -v(1,j): set by the BC passes, cleared by uploads
     // third-generation pressure solve (inner_gs3.cuh): full-height groups, diagonal streams
     bool gs3 = false;            // usable for this grid (SRCFD_GS3=0 disables)
-    int gs3_K = 3, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 8, gs3_grid = 0;
+    int gs3_K = 3, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 4, gs3_grid = 0;
     size_t gs3_smem = 0;
     const void* gs3_fn = nullptr;
     uint4* gs3_ll = nullptr;
@@ -268,6 +269,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
     cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
+    cudaFree(h->sweeps1); cudaFree(h->sweeps2);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -321,6 +323,8 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->halo2, halo_bytes));
     CKB(cudaMemsetAsync(h->halo2, 0, halo_bytes, h->stream));
     CKB(cudaMalloc(&h->scratch2, sizeof(double) * (P + pad)));
+    CKB(cudaMalloc(&h->sweeps1, sizeof(double) * (WF2_KMAX - 1) * (P + 8)));
+    CKB(cudaMalloc(&h->sweeps2, sizeof(double) * (WF2_KMAX - 1) * (P + 8)));
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
@@ -401,6 +405,16 @@ int srcfd_download(srcfd_handle* h, double* Var, double* VarOld, double* Ff, dou
     return SRCFD_OK;
 }
 
+int srcfd_host_alloc(uint64_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(SRCFD_ERR_ARG, "srcfd_host_alloc: null out or zero size");
+    *out = nullptr;
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return SRCFD_OK;
+}
+int srcfd_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return SRCFD_OK;
+}
 int srcfd_device_ptrs(srcfd_handle* h, uint64_t* Var, uint64_t* VarOld, uint64_t* Ff) {
     CKH(h);
     if (Var) *Var = (uint64_t)(uintptr_t)h->Var;
@@ -507,6 +521,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
         g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * WF3_RP; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
         g3.skip_idle = getenv("SRCFD_SKIP_IDLE") ? atoi(getenv("SRCFD_SKIP_IDLE")) : 1;
+        g3.pretouch = getenv("SRCFD_PRETOUCH") ? atoi(getenv("SRCFD_PRETOUCH")) : 1;
         void* args3[] = {&g3};
         CK(cudaLaunchCooperativeKernel(h->gs3_fn, dim3(h->gs3_grid), dim3(h->gs3_RP), args3, h->gs3_smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
@@ -516,8 +531,8 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         ga.trace = h->trace;
         ga.band_rows = P.band_rows; ga.nbands = P.nbands; ga.RS = P.RS; ga.ncomp = P.ncomp; ga.K = P.K;
         ga.np = pair ? 2 : 1;
-        ga.pr[0] = Gs2Prob{k, slot, h->scratch, h->partials, h->prog, h->halo};
-        ga.pr[1] = Gs2Prob{1, 1, h->scratch2, h->partials2, h->prog2, h->halo2};   // pair: k = slot = 0 above, 1 here
+        ga.pr[0] = Gs2Prob{k, slot, h->scratch, h->partials, h->prog, h->halo, h->sweeps1};
+        ga.pr[1] = Gs2Prob{1, 1, h->scratch2, h->partials2, h->prog2, h->halo2, h->sweeps2};   // pair: k = slot = 0 above, 1 here
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {

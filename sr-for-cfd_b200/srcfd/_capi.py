@@ -50,7 +50,8 @@ _lib = None
 SYMBOLS = [
     "srcfd_abi_version", "srcfd_last_error", "srcfd_device_count", "srcfd_create", "srcfd_destroy",
     "srcfd_set_params", "srcfd_synchronize", "srcfd_stream", "srcfd_upload", "srcfd_download",
-    "srcfd_device_ptrs", "srcfd_initialize_fields", "srcfd_set_fields", "srcfd_step", "srcfd_status",
+    "srcfd_device_ptrs", "srcfd_host_alloc", "srcfd_host_free", "srcfd_trace_read", "srcfd_debug_read",
+    "srcfd_initialize_fields", "srcfd_set_fields", "srcfd_step", "srcfd_status",
     "srcfd_reset_counters", "srcfd_solve", "srcfd_k_copy_new_to_old", "srcfd_k_apply_bc",
     "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
@@ -90,6 +91,34 @@ def device_count() -> int:
     n = C.c_int(0)
     rc = lib().srcfd_device_count(C.byref(n))
     return n.value if rc == OK else 0
+
+
+class _PinnedBuffer:
+    """Page-locked host block exposed through the buffer protocol; freed when the last numpy view goes away."""
+
+    def __init__(self, nbytes: int):
+        self.n = int(nbytes)
+        self.p = C.c_void_p()
+        check(lib().srcfd_host_alloc(C.c_uint64(self.n), C.byref(self.p)))
+
+    def __buffer__(self, flags):
+        return memoryview((C.c_char * self.n).from_address(self.p.value)).cast("B")
+
+    def __del__(self):
+        try:
+            if self.p:
+                lib().srcfd_host_free(self.p)
+                self.p = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype=np.float64) -> np.ndarray:
+    """np.zeros in page-locked memory (srcfd_host_alloc): same array semantics, full-rate upload/download."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    a = np.frombuffer(_PinnedBuffer(max(n, 1)), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    a[...] = 0
+    return a
 
 
 def _ptr(a):

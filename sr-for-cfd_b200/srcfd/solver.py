@@ -132,10 +132,11 @@ class CFDSolver:
         self.relaxed = bfs if relaxed is None else relaxed
         self.device, self.max_ctas = device, max_ctas
         self.nVar = 3
-        self.Var = np.zeros((self.nVar, mesh.nx + 2, mesh.ny + 2))
-        self.VarOld = np.zeros((self.nVar, mesh.nx + 2, mesh.ny + 2))
-        self.residual = np.zeros(self.nVar)
-        self.Ff = np.zeros((4, mesh.nx + 2, mesh.ny + 2))
+        # the reference's host arrays (LDC.py:340-345), page-locked so the per-call copies run at PCIe rate
+        self.Var = capi.pinned_zeros((self.nVar, mesh.nx + 2, mesh.ny + 2))
+        self.VarOld = capi.pinned_zeros((self.nVar, mesh.nx + 2, mesh.ny + 2))
+        self.residual = capi.pinned_zeros(self.nVar)
+        self.Ff = capi.pinned_zeros((4, mesh.nx + 2, mesh.ny + 2))
         self.residual_history = {'u': [], 'v': [], 'p': []}
         self.last_sweeps = np.zeros(3, dtype=np.int64)
         self.total_sweeps = np.zeros(3, dtype=np.int64)

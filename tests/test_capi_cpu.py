@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     txt = open(os.path.join(ROOT, "include", "srcfd.h")).read()
-    return sorted(set(re.findall(r"\b(srcfd_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(srcfd_[A-Za-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_and_library_agree():

@@ -14,8 +14,11 @@ for k in range(3):
 h = capi.Handle(p)
 rng = np.random.default_rng(0); Var = rng.uniform(-1, 1, (3, n + 2, n + 2)); Ff = 1e-3 * rng.uniform(-1, 1, (4, n + 2, n + 2))
 h.upload(Var, Var, Ff)
-for _ in range(2): h.upload(Var, Var, Ff); h.k_solve_pressure()
-K = 8
+MOM = os.environ.get("TRACE_OP", "pressure") != "pressure"      # TRACE_OP=momentum: the u solve (upwind) instead
+for _ in range(2):
+    h.upload(Var, Var, Ff); h.reset_counters()
+    print("sweeps, rms:", h.k_solve_momentum(0, 0) if MOM else h.k_solve_pressure())
+K = 4 if MOM else 8
 buf = np.zeros(((sweeps // 4 + 2) * 64 * 8), dtype=np.int64)
 capi.lib().srcfd_trace_read(h._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int64(buf.size))
 tr = buf.reshape(-1, 8); tr = tr[tr[:, 0] > 0]

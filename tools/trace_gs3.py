@@ -1,5 +1,5 @@
 """SRCFD_TRACE=1 python tools/trace_gs3.py [n] [sweeps]: per-group timeline of one full-height pressure solve."""
-import sys, os, ctypes as C
+import sys, os, time, ctypes as C
 os.environ["SRCFD_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sr-for-cfd_b200"))
@@ -14,7 +14,21 @@ for k in range(3):
     for s in range(4): p.bc_types[k][s] = 1 if k == 2 else 0
 h = capi.Handle(p)
 rng = np.random.default_rng(0); Var = rng.uniform(-1, 1, (3, n + 2, n + 2)); Ff = 1e-3 * rng.uniform(-1, 1, (4, n + 2, n + 2))
-for _ in range(3): h.upload(Var, Var, Ff); h.k_solve_pressure()
+flush = None
+if os.environ.get("FLUSH"):
+    import torch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    h.upload(Var, Var, Ff); h.synchronize()
+    if flush is not None:
+        if os.environ["FLUSH"] == "2": flush.sum()           # read-only sweep of 256 MiB: evicts without leaving dirty lines
+        else: flush.zero_()
+        if os.environ.get("FLUSH_BUSY"):                      # keep the SMs busy between the flush and the solve
+            xb = torch.randn(4096, 4096, device="cuda")
+            for _ in range(int(os.environ["FLUSH_BUSY"])): xb = (xb @ xb) * 1e-3
+        torch.cuda.synchronize()
+        if os.environ.get("FLUSH_SLEEP"): time.sleep(float(os.environ["FLUSH_SLEEP"]))
+    h.k_solve_pressure()
 buf = np.zeros(8 * 1024 + 64, dtype=np.int64)
 capi.lib().srcfd_trace_read(h._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int64(buf.size))
 G = (sweeps + K - 1) // K
@@ -29,6 +43,8 @@ if G > 1:
     lag_mid = np.diff(mid); lag_end = np.diff(end)
     print(f"group-to-group lag at mid: mean {lag_mid.mean():.2f} us (min {lag_mid.min():.2f} max {lag_mid.max():.2f}); at end: mean {lag_end.mean():.2f}")
     print(f"polls per group (all threads): mean {polls.mean():.0f}, first groups {polls[:6]}")
+    print("lag at mid by group decile:", np.round([lag_mid[i * len(lag_mid) // 10:(i + 1) * len(lag_mid) // 10].mean() for i in range(10)], 2))
     print("start of groups 0..5:", np.round(start[:6], 1), " ends:", np.round(end[:6], 1))
+    print("group 0: start/mid/end", np.round([start[0], mid[0], end[0]], 1), " group 10:", np.round([start[10], mid[10], end[10]], 1), " group 100:", np.round([start[100], mid[100], end[100]], 1))
     c = min(148, G - 1)
     print(f"group {c}: start {start[c]:.1f} (group {c-148 if c>=148 else 0} ended {end[max(c-148,0)]:.1f})")
