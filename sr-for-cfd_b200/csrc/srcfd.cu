@@ -206,7 +206,7 @@ static int plan_gs3(srcfd_handle* h) {
     const size_t per = sizeof(uint4) * (size_t)h->gs3_ND * WF3_RP;
     while (h->gs3_nbuf > 2 && per * h->gs3_nbuf > ((size_t)1 << 31)) --h->gs3_nbuf;
     if (per * h->gs3_nbuf > ((size_t)1 << 31)) return SRCFD_OK;
-    h->gs3_smem = sizeof(double) * ((size_t)3 * (WF3_KMAX + 1) * WF3_RP + 2 * (size_t)(ny + 2) + WF3_KMAX * 32);
+    h->gs3_smem = sizeof(double) * ((size_t)(3 * (WF3_KMAX + 1) + WF3_RQ) * WF3_RP + 2 * (size_t)(ny + 2) + WF3_KMAX * 32);
     if (h->gs3_smem > 200 * 1024) return SRCFD_OK;
     h->gs3_fn = RP <= 448 ? (const void*)k_solve_gs3<448> : (const void*)k_solve_gs3<512>;   // 448 threads: 144 registers each
     CK(cudaFuncSetAttribute(h->gs3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gs3_smem));

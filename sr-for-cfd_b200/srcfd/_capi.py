@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsrcfd.so")
+# SRCFD_LIB: an alternative build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("SRCFD_LIB") or os.path.join(_HERE, "_lib", "libsrcfd.so")
 
 SCHEME_UPWIND, SCHEME_QUICK = 0, 1
 ORDER_GS_LEX, ORDER_JACOBI, ORDER_RED_BLACK = 0, 1, 2
