@@ -556,9 +556,12 @@ static int l_implicit_solve(srcfd_handle* h) {
     // The u and v momentum solves are independent (different planes, same read-only Ff): one paired wavefront
     // launch when the reference order is in use.  The BFS inlet pass for k = 0 also rewrites the v ghost column
     // (BFS.py:562) from the current v; that is a no-op exactly when the ghosts are fresh, so pair only then.
+    // With stale ghosts the v solve must still see the refreshed column (applied up front, mode 4); only QUICK's u solve
+    // also READS that column (flat over-read of row nx+2, hazard H4), so QUICK pairs only when the ghosts are fresh.
     const bool pair = h->pair_momentum && h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 &&
-                      (!h->bc.bfs || h->ghosts_fresh);
+                      (!h->bc.bfs || h->ghosts_fresh || mop == OP_UPWIND);
     if (pair) {
+        if (h->bc.bfs && !h->ghosts_fresh) TRY(l_apply_bc(h, 0, 4));
         TRY(l_inner_solve(h, mop, 0, 0, true));
         for (int k = 0; k < 2; ++k) {
             if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));

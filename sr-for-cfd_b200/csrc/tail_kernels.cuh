@@ -33,6 +33,15 @@ __global__ void k_apply_bc(double* __restrict__ Var, int k, Consts K, BcSpec bc,
     const bool generic = (mode != 2), inlet = (mode != 1) && bc.bfs && (k == 0 || k == 1);
     const int t = blockIdx.x * blockDim.x + threadIdx.x + 1;
     double* V = Var + (long long)k * K.plane;
+    if (mode == 4) {
+        // only the side effect of the k = 0 inlet pass on the v ghost column (BFS.py:562), so that a paired u/v solve
+        // sees the column the reference's v solve would see
+        if (bc.bfs && t <= K.ny && (t - 0.5) * K.dy >= bc.step_h) {
+            double* Vv = Var + K.plane;
+            Vv[t] = -Vv[K.pitch + t];
+        }
+        return;
+    }
     if (t <= K.ny) {
         const int j = t;
         if (generic) {

@@ -244,6 +244,29 @@ def test_stepwise_api_matches_solve():
     assert np.array_equal(a.Var, b.Var) and np.array_equal(a.VarOld, b.VarOld) and np.array_equal(a.Ff, b.Ff)
 
 
+@pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
+def test_bfs_implicit_solve_with_arbitrary_ghosts(scheme):
+    """The host-array path uploads whatever the caller holds, ghost cells included.  The paired u/v momentum launch must
+    then still give the reference's result: the k=0 inlet pass rewrites part of the v ghost column BEFORE the v solve
+    (BFS.py:562), and QUICK's u solve over-reads that column (hazard H4)."""
+    from srcfd import bfs
+    nx, ny = 40, 30
+    rng = np.random.default_rng(3)
+    s = bfs.CFDSolver(bfs.MeshParameters(nx=nx, ny=ny), bfs.FluidProperties(Re=400.0),
+                      bfs.SolverSettings(dt=2e-3, scheme=scheme, max_iterations=4), _bfs_bc(bfs))
+    o = O.OracleSolver(O.bfs_case(nx, ny, scheme=scheme))
+    for it in range(3):
+        V = 0.1 * rng.uniform(-1, 1, s.Var.shape); Vo = V + 0.01 * rng.uniform(-1, 1, V.shape)
+        F = 0.01 * rng.uniform(-1, 1, s.Ff.shape)
+        s.Var[...] = V; s.VarOld[...] = Vo; s.Ff[...] = F
+        o.Var[...] = V; o.VarOld[...] = Vo; o.Ff[...] = F
+        s._implicit_solve(); sw = o.implicit_solve()
+        assert s.last_sweeps.tolist() == sw.tolist()
+        assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff), (scheme, it, np.max(np.abs(s.Var - o.Var)))
+        s._implicit_solve(); sw = o.implicit_solve()          # second call: same arrays, now with consistent ghosts
+        assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
+
+
 def test_nan_raises_value_error():
     from srcfd import ldc
     s = ldc.CFDSolver(ldc.MeshParameters(nx=16, ny=16), ldc.FluidProperties(Re=100.0),
