@@ -60,10 +60,11 @@ def peaks():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per pressure-solve launch from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "ncu_pressure_r01.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+    for name in ("ncu_pressure_r01c.json", "ncu_pressure_r01.json"):     # latest capture of the kernel in use first
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f).get("dram_bytes_per_launch")
     return None
 
 
