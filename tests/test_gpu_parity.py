@@ -231,6 +231,30 @@ def test_composed_solver_vs_oracle(order, ocode):
     np.testing.assert_allclose(np.sqrt(s.residual / (nx * ny)) / 1e-3, rms, rtol=1e-12)
 
 
+@pytest.mark.slow
+def test_full_size_400x400_outer_iterations_bit_exact():
+    """BASELINE's own grid: two whole outer iterations of the BFS Re=400 UPWIND case and of the LDC Re=100 QUICK case on
+    400 x 400 (1000-sweep pressure solves through the full-height kernel, paired momentum launch), bit for bit against
+    the oracle, plus a linearity-free size-independent check: the sweep counters and the residual norms."""
+    from srcfd import bfs, ldc
+    nx = ny = 400
+    s = bfs.CFDSolver(bfs.MeshParameters(nx=nx, ny=ny), bfs.FluidProperties(Re=400.0),
+                      bfs.SolverSettings(dt=2e-3, max_iterations=2), _bfs_bc(bfs))
+    n, _ = s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.bfs_case(nx, ny))
+    m, rms, _ = o.solve(2)
+    assert n == m == 2 and s.total_sweeps.tolist() == o.total_sweeps.tolist()
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff) and np.array_equal(s.VarOld, o.VarOld)
+    np.testing.assert_allclose(np.sqrt(s.residual / (nx * ny)) / 2e-3, rms, rtol=1e-12)
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=nx, ny=ny), ldc.FluidProperties(Re=100.0),
+                      ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=2), ldc.BoundaryConditions())
+    n, _ = s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme="QUICK"))
+    m, rms, _ = o.solve(2)
+    assert n == m == 2 and s.total_sweeps.tolist() == o.total_sweeps.tolist()
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
+
+
 def test_stepwise_api_matches_solve():
     """_implicit_solve / _convergence_check (host-array API) == solve()."""
     from srcfd import bfs
