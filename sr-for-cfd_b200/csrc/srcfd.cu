@@ -15,6 +15,7 @@
 #include "inner_solvers.cuh"
 #include "inner_gs2.cuh"
 #include "inner_gs3.cuh"
+#include "jacobi_tb.cuh"
 
 using namespace srcfd;
 
@@ -78,6 +79,11 @@ struct srcfd_handle {
     uint4* gs3_ll = nullptr;
     double* gs3_rhsS = nullptr;
     unsigned long long* gs3_epoch = nullptr;
+    // temporally blocked Jacobi pressure solve (jacobi_tb.cuh); SRCFD_JTB=0 falls back to one sweep per grid barrier
+    int jtb_H = 0, jtb_grid = 0;
+    size_t jtb_smem = 0;
+    const void* jtb_fn = nullptr;
+    double* jtb_partials = nullptr;
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
@@ -219,8 +225,28 @@ static int plan_gs3(srcfd_handle* h) {
     return SRCFD_OK;
 }
 
+static int plan_jtb(srcfd_handle* h) {
+    h->jtb_H = 0;
+    if (const char* e = getenv("SRCFD_JTB")) if (atoi(e) == 0) return SRCFD_OK;
+    const long long ncell = (long long)h->p.nx * h->p.ny;
+    int H = ncell >= (1 << 20) ? 4 : 8;      // large planes are fp64-bound (less redundant halo work), small ones barrier-bound
+    if (const char* e = getenv("SRCFD_JTB_H")) H = atoi(e) == 4 ? 4 : 8;
+    h->jtb_fn = H == 4 ? (const void*)k_jacobi_tb<4> : (const void*)k_jacobi_tb<8>;
+    h->jtb_smem = H == 4 ? JtbShape<4>::smem : JtbShape<8>::smem;
+    CK(cudaFuncSetAttribute(h->jtb_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->jtb_smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->jtb_fn, JTB_THREADS, h->jtb_smem));
+    if (occ < 1) return SRCFD_OK;
+    const long long tiles = (long long)((h->p.nx + JTB_TI - 1) / JTB_TI) * ((h->p.ny + JTB_TJ - 1) / JTB_TJ);
+    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+    h->jtb_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(cap, (long long)occ * h->num_sms), tiles));
+    h->jtb_H = H;
+    return SRCFD_OK;
+}
+
 static int plan_launches(srcfd_handle* h) {
     if (int rc = plan_gs3(h)) return rc;
+    if (int rc = plan_jtb(h)) return rc;
     for (int op = 0; op < 3; ++op) if (int rc = plan_gs2(h, op)) return rc;
     const int nx = h->p.nx;
     h->nbands = (nx + WF_MAX_BAND - 1) / WF_MAX_BAND;
@@ -268,6 +294,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
+    cudaFree(h->jtb_partials);
     cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
     cudaFree(h->sweeps1); cudaFree(h->sweeps2);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
@@ -328,6 +355,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
+    if (h->jtb_H) CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1)));
     if (h->gs3) {
         const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
         CKB(cudaMalloc(&h->gs3_ll, llb));
@@ -537,6 +565,11 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
         CK(cudaLaunchCooperativeKernel(pick_gs(op), dim3(h->grid_gs[op]), dim3(h->wf_threads), args, h->wf_smem, h->stream));
+    } else if (h->p.sweep_order == SRCFD_ORDER_JACOBI && op == OP_PRESSURE && h->jtb_H) {
+        JtbArgs ja;
+        ja.s = a; ja.partials = h->jtb_partials;
+        void* argsj[] = {&ja};
+        CK(cudaLaunchCooperativeKernel(h->jtb_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), argsj, h->jtb_smem, h->stream));
     } else {
         if (h->p.sweep_order == SRCFD_ORDER_RED_BLACK && op == OP_QUICK)
             return fail(SRCFD_ERR_ARG, "red-black order is undefined for QUICK");

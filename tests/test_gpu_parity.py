@@ -138,6 +138,45 @@ def test_pressure_kernel_generations_bit_exact(K, env, monkeypatch):
         kernels._cache.clear()
 
 
+@pytest.mark.parametrize("env", [{"SRCFD_JTB_H": "8"}, {"SRCFD_JTB_H": "4"}, {"SRCFD_JTB": "0"}])
+def test_jacobi_temporally_blocked_pressure_bit_exact(K, env, monkeypatch):
+    """JACOBI order (opt-in): the temporally blocked kernel (H sweeps per pass through shared-memory tiles with halos) and
+    the one-sweep-per-barrier kernel against the oracle's Jacobi restatement -- partial tiles, planes smaller than a
+    tile, sweep caps that are not multiples of H, and early stops inside a pass (the pass is repeated with fewer sweeps)."""
+    from srcfd import kernels
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    for h in kernels._cache.values():
+        h.close()
+    kernels._cache.clear()
+    try:
+        for (Nx, Ny), caps in (((64, 48), (1, 7, 16, 61)), ((33, 130), (5, 24)), ((100, 129), (19,)), ((1, 1), (3,)), ((2, 3), (9,)),
+                               ((300, 70), (12,))):
+            Var, VarOld, Ff = rnd_state(21 + Nx + Ny, Nx, Ny)
+            dx, dy = 1.3 / Nx, 0.9 / Ny
+            for cap in caps:
+                A, B = Var.copy(), Var.copy()
+                n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, 2e-3, 1.0, dx * dy, sweep_order="JACOBI", max_iter=cap)
+                m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, 2e-3, 1.0, dx * dy, order=O.ORDER_JACOBI, max_iter=cap)
+                assert n == m and np.array_equal(A, B), (env, Nx, Ny, cap, n, m, np.max(np.abs(A - B)))
+        Nx, Ny = 40, 30
+        Var, VarOld, Ff = rnd_state(5, Nx, Ny, ff_scale=1e-4)
+        Var[2] *= 1e-3
+        dx, dy = 1.0 / Nx, 1.0 / Ny
+        counts = []
+        for tol in (1e-2, 1e-6, 1e-3, 1e-7, 1e-4, 3e-5):
+            A, B = Var.copy(), Var.copy()
+            n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, sweep_order="JACOBI", tolerance=tol, max_iter=900)
+            m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, order=O.ORDER_JACOBI, tolerance=tol, max_iter=900)
+            assert n == m and np.array_equal(A, B), (env, tol, n, m)
+            counts.append(n)
+        assert len(set(counts)) >= 4, counts
+    finally:
+        for h in kernels._cache.values():
+            h.close()
+        kernels._cache.clear()
+
+
 def test_break_semantics_and_rollback(K):
     """Exact 'stop after the first sweep with rms < tol' behaviour, including the speculative-group
     rollback of the wavefront order (the cached handle carries the previous call's sweep count as its guess)."""
