@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include <algorithm>
 #include <cuda_runtime.h>
@@ -48,8 +49,6 @@ __global__ void k_dense(const float* __restrict__ in, const float* __restrict__ 
 // Conv2D, cross-correlation, zero padding (pt, pl) at the top/left; W (kh, kw, Cin, Cout)
 template <typename TIN>
 __device__ __forceinline__ float ld_act(const TIN* p) { return (float)*p; }
-template <>
-__device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 template <typename TIN>
 __global__ void k_conv2d(const TIN* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
@@ -76,6 +75,83 @@ __global__ void k_conv2d(const TIN* __restrict__ in, const float* __restrict__ W
     }
     acc += bias[co];
     out[t] = act ? swishf(acc) : acc;
+}
+
+// Final layer of decoder_400: Conv2D(1, 3x3, 'same', linear) on (B, H, W, 8) -> (B, H, W, 1).  HBM-bound (2.56 MB of bf16
+// in, 0.64 MB out per sample): a CTA stages an (18 x 66) pixel tile with its halo in shared memory (one 16-byte or
+// 32-byte vector per pixel), every thread produces 4 vertically adjacent outputs so each staged row is read once per
+// three taps, weights (72 floats) sit in registers.  W layout (3, 3, 8, 1).
+constexpr int FC_TX = 64, FC_TY = 16;
+template <typename TIN>
+__global__ void __launch_bounds__(256) k_conv3x3_c8_final(const TIN* __restrict__ in, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd) {
+    __shared__ float tile[(FC_TY + 2) * (FC_TX + 2) * 8];       // staged as fp32 (19 KB... 38 KB): one conversion per input value
+    const int b = blockIdx.z, y0 = blockIdx.y * FC_TY, x0 = blockIdx.x * FC_TX;
+    const TIN* src = in + (long long)b * H * Wd * 8;
+    // all vector loads of the tile are in flight before the first conversion/store (one memory round trip per CTA)
+    constexpr int NPIX = (FC_TY + 2) * (FC_TX + 2), PER = (NPIX + 255) / 256;
+    using VecT = typename std::conditional<sizeof(TIN) == 2, uint4, float4>::type;     // 8 bf16, or 4 of the 8 floats
+    VecT va[PER], vb[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int p = threadIdx.x + q * 256;
+        const int ty = p / (FC_TX + 2), tx = p - ty * (FC_TX + 2);
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
+        va[q] = VecT{}; vb[q] = VecT{};
+        if (p < NPIX && y >= 0 && y < H && x >= 0 && x < Wd) {
+            const VecT* qv = reinterpret_cast<const VecT*>(src + ((long long)y * Wd + x) * 8);
+            va[q] = __ldg(qv);
+            if constexpr (sizeof(TIN) != 2) vb[q] = __ldg(qv + 1);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int p = threadIdx.x + q * 256;
+        if (p >= NPIX) continue;
+        float v[8];
+        if constexpr (sizeof(TIN) == 2) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&va[q]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const float2 f = __bfloat1622float2(h2[c]); v[2 * c] = f.x; v[2 * c + 1] = f.y; }
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(&va[q]), c4 = *reinterpret_cast<const float4*>(&vb[q]);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+        }
+        float4* d = reinterpret_cast<float4*>(tile + (size_t)p * 8);
+        d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    float w[72];
+#pragma unroll
+    for (int i = 0; i < 72; ++i) w[i] = W[i];
+    const float bs = bias[0];
+    __syncthreads();
+    const int tx = threadIdx.x & (FC_TX - 1), tq = threadIdx.x / FC_TX;        // 4 row groups of 4 rows
+    float acc[4] = {bs, bs, bs, bs};
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {                                               // staged rows 4*tq + r feed outputs r-2 .. r
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float4* q = reinterpret_cast<const float4*>(tile + ((size_t)(4 * tq + r) * (FC_TX + 2) + tx + kx) * 8);
+            const float4 a = q[0], c4 = q[1];
+            const float xv[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int ky = r - o;
+                if (ky >= 0 && ky < 3) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[o] = fmaf(xv[c], w[(ky * 3 + kx) * 8 + c], acc[o]);
+                }
+            }
+        }
+    }
+    const int x = x0 + tx;
+    if (x < Wd) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int y = y0 + 4 * tq + o;
+            if (y < H) out[((long long)b * H + y) * Wd + x] = acc[o];
+        }
+    }
 }
 
 // Conv2DTranspose 'valid' in gather form; Wt (kh, kw, Cin, Cout) (= Keras (kh, kw, Cout, Cin) transposed at upload)
@@ -206,7 +282,7 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
             k_conv2d_transpose<<<nblk((long long)B * hw[l + 1] * hw[l + 1] * ch[l + 1]), 256, 0, h->stream>>>(
                 h->act[l], h->dec[l + 1].W, h->dec[l + 1].b, h->act[l + 1], B, hw[l], hw[l], ch[l], hw[l + 1], hw[l + 1], ch[l + 1], k, 2, 1);
         }
-        k_conv2d<float><<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
+        k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400);
         h->launches += 6;
     } else {
         // ConvT1 (3x3, stride 2: overlapping taps): tensor-core GEMM per tap into Y (act[5] reused as fp32 scratch,
@@ -223,7 +299,7 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         h->launches += 2;
         for (int l = 1; l <= 4; ++l)
             if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
-        k_conv2d<__nv_bfloat16><<<nblk((long long)B * 400 * 400), 256, 0, h->stream>>>(h->actbf[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400, 8, 400, 400, 1, 3, 3, 1, 1, 1, 0);
+        k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400);
         h->launches += 1;
     }
     SRCK(cudaGetLastError());
@@ -311,7 +387,7 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
 
 static int sr_run(srcfd_sr* h, const float* x, const float* z, int B, float* zout, float* out) {
     SRCK(cudaSetDevice(h->dev));
-    const int CH = std::min(B, 32);
+    const int CH = std::min(B, 128);     // samples per pass: large enough that the early (small) layers fill the GPU
     if (int rc = ensure_chunk(h, CH)) return rc;
     float* zdev = h->zin + (size_t)h->chunk * 128;   // latents (CH,50) live behind the (chunk,128) dense scratch
     for (int b0 = 0; b0 < B; b0 += CH) {
@@ -356,7 +432,7 @@ int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev,
     if (!h || !z_dev || !out_dev || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
     if (!h->has_dec) return sr_fail(SRCFD_ERR_ARG, "decoder weights not set");
     SRCK(cudaSetDevice(h->dev));
-    const int CH = std::min(B, 32);
+    const int CH = std::min(B, 128);     // samples per pass: large enough that the early (small) layers fill the GPU
     if (int rc = ensure_chunk(h, CH)) return rc;
     SRCK(cudaEventRecord(h->ea, h->stream));
     for (int b0 = 0; b0 < B; b0 += CH) {
