@@ -82,9 +82,10 @@ __global__ void k_conv2d(const TIN* __restrict__ in, const float* __restrict__ W
 // 32-byte vector per pixel), every thread produces 4 vertically adjacent outputs so each staged row is read once per
 // three taps, weights (72 floats) sit in registers.  W layout (3, 3, 8, 1).
 constexpr int FC_TX = 64, FC_TY = 16;
+struct FinalConvW { float w[72]; float b; };      // passed by value: lives in the constant bank, no registers
 template <typename TIN>
-__global__ void __launch_bounds__(256) k_conv3x3_c8_final(const TIN* __restrict__ in, const float* __restrict__ W,
-                                                          const float* __restrict__ bias, float* __restrict__ out, int B, int H, int Wd) {
+__global__ void __launch_bounds__(256, 4) k_conv3x3_c8_final(const TIN* __restrict__ in, const FinalConvW fw, float* __restrict__ out,
+                                                             int B, int H, int Wd) {
     __shared__ float tile[(FC_TY + 2) * (FC_TX + 2) * 8];       // staged as fp32 (19 KB... 38 KB): one conversion per input value
     const int b = blockIdx.z, y0 = blockIdx.y * FC_TY, x0 = blockIdx.x * FC_TX;
     const TIN* src = in + (long long)b * H * Wd * 8;
@@ -120,10 +121,7 @@ __global__ void __launch_bounds__(256) k_conv3x3_c8_final(const TIN* __restrict_
         float4* d = reinterpret_cast<float4*>(tile + (size_t)p * 8);
         d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    float w[72];
-#pragma unroll
-    for (int i = 0; i < 72; ++i) w[i] = W[i];
-    const float bs = bias[0];
+    const float bs = fw.b;
     __syncthreads();
     const int tx = threadIdx.x & (FC_TX - 1), tq = threadIdx.x / FC_TX;        // 4 row groups of 4 rows
     float acc[4] = {bs, bs, bs, bs};
@@ -139,7 +137,7 @@ __global__ void __launch_bounds__(256) k_conv3x3_c8_final(const TIN* __restrict_
                 const int ky = r - o;
                 if (ky >= 0 && ky < 3) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[o] = fmaf(xv[c], w[(ky * 3 + kx) * 8 + c], acc[o]);
+                    for (int c = 0; c < 8; ++c) acc[o] = fmaf(xv[c], fw.w[(ky * 3 + kx) * 8 + c], acc[o]);
                 }
             }
         }
@@ -198,6 +196,7 @@ struct srcfd_sr {
     int precision = 0;                 // 0: fp32 CUDA cores everywhere; 1: bf16 tcgen05 for the four 2x2/stride-2 ConvT layers
     __nv_bfloat16* actbf[6] = {nullptr};   // bf16 activations of layers 1..5 (index = layer) for one chunk
     int* tc_err = nullptr;
+    FinalConvW fcw;                    // host copy of the last layer's 72 weights + bias (kernel argument)
 };
 
 namespace {
@@ -282,7 +281,7 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
             k_conv2d_transpose<<<nblk((long long)B * hw[l + 1] * hw[l + 1] * ch[l + 1]), 256, 0, h->stream>>>(
                 h->act[l], h->dec[l + 1].W, h->dec[l + 1].b, h->act[l + 1], B, hw[l], hw[l], ch[l], hw[l + 1], hw[l + 1], ch[l + 1], k, 2, 1);
         }
-        k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400);
+        k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->fcw, out_dev, B, 400, 400);
         h->launches += 6;
     } else {
         // ConvT1 (3x3, stride 2: overlapping taps): tensor-core GEMM per tap into Y (act[5] reused as fp32 scratch,
@@ -299,7 +298,7 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         h->launches += 2;
         for (int l = 1; l <= 4; ++l)
             if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
-        k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->dec[6].W, h->dec[6].b, out_dev, B, 400, 400);
+        k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->fcw, out_dev, B, 400, 400);
         h->launches += 1;
     }
     SRCK(cudaGetLastError());
@@ -380,6 +379,7 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
     }
     if (int rc = upload(&h->dec[6].W, kernels[6], 3 * 3 * 8 * 1, h->stream)) return rc;
     if (int rc = upload(&h->dec[6].b, biases[6], 1, h->stream)) return rc;
+    memcpy(h->fcw.w, kernels[6], 72 * sizeof(float)); h->fcw.b = biases[6][0];
     SRCK(cudaStreamSynchronize(h->stream));
     h->has_dec = true;
     return SRCFD_OK;
