@@ -249,8 +249,8 @@ int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* W
                     int B, int H) {
     const long long M = (long long)B * H * H;
     const size_t smem = srtc::convT_tc_smem<KD, ND>();
-    static bool attr_done = false;
-    if (!attr_done) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<KD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    static bool attr_done[64] = {false};                 // per device: the attribute belongs to the (device, kernel) pair
+    if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<KD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
     srtc::k_convT2x2_tc<KD, ND><<<(unsigned)((M + 127) / 128), 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
     h->launches += 1;
     SRCK(cudaGetLastError());
@@ -289,8 +289,8 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         {
             const long long M = (long long)B * 144;
             const size_t smem = srtc::convT_tc_smem<256, 128>();
-            static bool attr_done = false;
-            if (!attr_done) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<256, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+            static bool attr_done[64] = {false};
+            if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<256, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
             srtc::k_convT2x2_tc<256, 128, 1><<<dim3((unsigned)((M + 127) / 128), 9), 128, smem, h->stream>>>(
                 h->actbf[0], h->dec[1].Wbf, h->dec[1].b, nullptr, M, 12, 12, h->tc_err, h->act[5], 1152);
             srtc::k_col2im_3x3s2<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->actbf[1], B);

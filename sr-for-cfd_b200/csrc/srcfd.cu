@@ -6,6 +6,8 @@
 #include <cmath>
 #include <chrono>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/srcfd.h"
@@ -156,6 +158,20 @@ template <int OP> static void shape2(int& K, int& NB, int& MAXT, int& NAUX, int&
 
 // Row bands for the K-sweep wavefront: (K+1) thread groups of RS slots each (+ service warps) must fit the
 // CTA, and every band needs >= NB*K rows so that the redundant rows of the band above stay inside it.
+// The opt-in dynamic shared-memory limit is a per-(device, kernel) attribute shared by every handle of the process:
+// only ever raise it, or a handle created later for a smaller grid would break the launches of an earlier one.
+static int raise_smem_limit(int dev, const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    std::lock_guard<std::mutex> g(mu);
+    size_t& c = cur[std::make_pair(dev, fn)];
+    if (bytes > c) {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        c = bytes;
+    }
+    return SRCFD_OK;
+}
+
 static int plan_gs2(srcfd_handle* h, int op) {
     int KT, NB, MAXT, NAUX, AD;
     if (op == OP_PRESSURE) shape2<OP_PRESSURE>(KT, NB, MAXT, NAUX, AD);
@@ -188,7 +204,7 @@ static int plan_gs2(srcfd_handle* h, int op) {
         P.smem = sizeof(double) * ((size_t)(WF2_RING + 1) * P.ncomp + (size_t)NAUX * AD * P.RS);
         if (P.nthreads > MAXT) continue;
         int occ = 0;
-        CK(cudaFuncSetAttribute(pick_gs2(op), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        if (int rc = raise_smem_limit(h->dev, pick_gs2(op), P.smem)) return rc;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_gs2(op), P.nthreads, P.smem));
         if (occ < 1) continue;
         const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
@@ -215,7 +231,7 @@ static int plan_gs3(srcfd_handle* h) {
     h->gs3_smem = sizeof(double) * ((size_t)(3 * (WF3_KMAX + 1) + WF3_RQ) * WF3_RP + 2 * (size_t)(ny + 2) + WF3_KMAX * 32);
     if (h->gs3_smem > 200 * 1024) return SRCFD_OK;
     h->gs3_fn = RP <= 448 ? (const void*)k_solve_gs3<448> : (const void*)k_solve_gs3<512>;   // 448 threads: 144 registers each
-    CK(cudaFuncSetAttribute(h->gs3_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gs3_smem));
+    if (int rc = raise_smem_limit(h->dev, h->gs3_fn, h->gs3_smem)) return rc;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->gs3_fn, RP, h->gs3_smem));
     if (occ < 1) return SRCFD_OK;
@@ -233,7 +249,7 @@ static int plan_jtb(srcfd_handle* h) {
     if (const char* e = getenv("SRCFD_JTB_H")) H = atoi(e) == 4 ? 4 : 8;
     h->jtb_fn = H == 4 ? (const void*)k_jacobi_tb<4> : (const void*)k_jacobi_tb<8>;
     h->jtb_smem = H == 4 ? JtbShape<4>::smem : JtbShape<8>::smem;
-    CK(cudaFuncSetAttribute(h->jtb_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->jtb_smem));
+    if (int rc = raise_smem_limit(h->dev, h->jtb_fn, h->jtb_smem)) return rc;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->jtb_fn, JTB_THREADS, h->jtb_smem));
     if (occ < 1) return SRCFD_OK;

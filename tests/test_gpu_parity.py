@@ -126,6 +126,13 @@ def test_pressure_kernel_generations_bit_exact(K, env, monkeypatch):
             assert n == m and np.array_equal(A, B), (env, tol, n, m)
             counts.append(n)
         assert len(set(counts)) >= 3, counts
+        # limits of the full-height kernel: 481 rows and sweep caps >= 4094 take the banded kernel; results must not change
+        for (nx2, ny2, cap, tol) in ((481, 6, 9, 1e-6), (20, 20, 4500, 1e-6)):
+            V2, _, F2 = rnd_state(3 + nx2, nx2, ny2, ff_scale=1e-3)
+            A, B = V2.copy(), V2.copy()
+            n = K.solve_pressure(A, F2, nx2, ny2, 1.0 / nx2, 1.0 / ny2, 1e-3, 1.0, 1.0 / (nx2 * ny2), tolerance=tol, max_iter=cap)
+            m = O.solve_pressure(B, F2, nx2, ny2, 1.0 / nx2, 1.0 / ny2, 1e-3, 1.0, 1.0 / (nx2 * ny2), tolerance=tol, max_iter=cap)
+            assert n == m and np.array_equal(A, B), (env, nx2, ny2, cap, n, m)
         # zero field: the reciprocal fast path is out of range for 0/b and the IEEE path must give the same bits
         Z = np.zeros_like(Var); Fz = Ff.copy()
         A, B = Z.copy(), Z.copy()
