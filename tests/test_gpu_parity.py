@@ -337,6 +337,25 @@ def test_bfs_implicit_solve_with_arbitrary_ghosts(scheme):
         assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
 
 
+@pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
+def test_ldc_implicit_solve_host_arrays_with_arbitrary_ghosts(scheme):
+    """Same for the cavity (no inlet override, no relaxation calls): _implicit_solve on whatever the host arrays hold."""
+    from srcfd import ldc
+    nx, ny = 36, 44
+    rng = np.random.default_rng(8)
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=nx, ny=ny), ldc.FluidProperties(Re=100.0),
+                      ldc.SolverSettings(dt=1e-3, scheme=scheme, max_iterations=4), ldc.BoundaryConditions())
+    o = O.OracleSolver(O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme=scheme))
+    for it in range(2):
+        V = 0.1 * rng.uniform(-1, 1, s.Var.shape); Vo = V + 0.01 * rng.uniform(-1, 1, V.shape)
+        F = 0.01 * rng.uniform(-1, 1, s.Ff.shape)
+        s.Var[...] = V; s.VarOld[...] = Vo; s.Ff[...] = F
+        o.Var[...] = V; o.VarOld[...] = Vo; o.Ff[...] = F
+        s._implicit_solve(); sw = o.implicit_solve()
+        assert s.last_sweeps.tolist() == sw.tolist()
+        assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff), (scheme, it, np.max(np.abs(s.Var - o.Var)))
+
+
 def test_nan_raises_value_error():
     from srcfd import ldc
     s = ldc.CFDSolver(ldc.MeshParameters(nx=16, ny=16), ldc.FluidProperties(Re=100.0),
