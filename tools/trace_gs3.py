@@ -7,7 +7,7 @@ import numpy as np
 from srcfd import _capi as capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-K = int(os.environ.get("SRCFD_K3", "4"))
+K = int(os.environ.get("SRCFD_K3", "3"))
 p = capi.Params(); p.nx = p.ny = n; p.dx = p.dy = 1.0 / n; p.volp = p.dx * p.dy; p.dt = 1e-3; p.nu = 1e-2; p.rho = 1.0
 p.inner_tol = 0.0; p.inner_max = sweeps
 for k in range(3):
