@@ -113,6 +113,16 @@ int srcfd_k_update_flux(srcfd_handle *h);                             /* LDC.py:
 int srcfd_k_under_relax(srcfd_handle *h, int k, double alpha);        /* BFS.py:371-375 */
 int srcfd_k_correct_velocity(srcfd_handle *h, double residual_out[3]);/* LDC.py:316-328 (residual += sums) */
 int srcfd_k_solve_pressure(srcfd_handle *h, int32_t *sweeps, double *last_rms);          /* LDC.py:292-314 */
+/* One temporally blocked JACOBI pass of the pressure relaxation on its own (slab decomposition, srcfd/slab.py):
+ * nsweeps (1..srcfd_jacobi_pass_max) sweeps of plane 2 in place, every cell of a sweep from the previous iterate
+ * (LDC.py:300-310 with ORDER_JACOBI of the oracle); sums[t] = sum of R^2 of sweep t over interior rows own_row0..own_row1
+ * (1-based, inclusive: a slab's halo rows are relaxed but not counted).  recompute_rhs != 0 rebuilds the right-hand
+ * side from Ff first, as solve_pressure does (LDC.py:305).  commit == 0 leaves the plane untouched (the result waits in
+ * the scratch plane) so that the caller can apply the break rule to the globally reduced sums first: accept with
+ * srcfd_k_jacobi_commit, or repeat the pass with fewer sweeps. */
+int srcfd_jacobi_pass_max(srcfd_handle *h, int *H);
+int srcfd_k_jacobi_pass(srcfd_handle *h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, double *sums);
+int srcfd_k_jacobi_commit(srcfd_handle *h);
 int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, double *last_rms); /* LDC.py:248-290 */
 /* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
 int srcfd_k_implicit_solve(srcfd_handle *h);

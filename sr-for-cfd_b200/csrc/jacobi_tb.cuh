@@ -32,7 +32,7 @@ struct JtbShape {
 // One pass: nsw (<= H) sweeps from plane src to plane dst; acc[t] += sum of R^2 of sweep t over this CTA's owned cells.
 template <int H>
 __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, double* __restrict__ dst, const int nsw,
-                         double* sm, double* acc, const Gs3Div& D) {
+                         double* sm, double* acc, const Gs3Div& D, const int res_r0, const int res_r1) {
     constexpr int RI = JtbShape<H>::RI, RJ = JtbShape<H>::RJ;
     const Consts& K = a.K;
     double* b0 = sm;
@@ -118,7 +118,7 @@ __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, dou
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             nxt[idx + q * RJ] = nv[q];
-                            if (own_col && li + q >= H && li + q < H + JTB_TI) part += R[q] * R[q];    // owned cell
+                            if (own_col && li + q >= H && li + q < H + JTB_TI && gi0 + li + q >= res_r0 && gi0 + li + q <= res_r1) part += R[q] * R[q];    // owned cell
                         }
                         im = v[4]; c = v[5];
                     }
@@ -133,7 +133,7 @@ __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, dou
                             nv = o.x; R = o.y;
                         }
                         nxt[idx] = nv;
-                        if (own_col && li >= H && li < H + JTB_TI) part += R * R;      // owned cell
+                        if (own_col && li >= H && li < H + JTB_TI && gi0 + li >= res_r0 && gi0 + li <= res_r1) part += R * R;      // owned cell
                         im = c; c = ip;
                     }
                 }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb(JtbArgs ja) {
             double acc[H];
 #pragma unroll
             for (int t = 0; t < H; ++t) acc[t] = 0.0;
-            jtb_pass<H>(a, src, dst, nsw, smem, acc, D);
+            jtb_pass<H>(a, src, dst, nsw, smem, acc, D, 1, K.nx);
             double* part = ja.partials + (size_t)(pass & 1) * H * gridDim.x;
             ++pass;
 #pragma unroll
@@ -220,6 +220,49 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb(JtbArgs ja) {
         a.ctrl->last_sweeps[a.slot] = n;
         a.ctrl->total_sweeps[a.slot] += n;
         a.ctrl->last_inner_rms[a.slot] = rms;
+    }
+}
+
+// ---- one pass on its own (slab decomposition, srcfd/slab.py): no grid-wide barrier, so an ordinary launch -------------
+// nsw (<= H) sweeps from the plane to the scratch plane; per-CTA residual sums of every sweep, counted over rows
+// [res_r0, res_r1] only (a slab's halo rows are relaxed too, but belong to the neighbour).
+template <int H>
+__global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int nsw, int res_r0, int res_r1) {
+    const SolveArgs& a = ja.s;
+    if (a.ctrl->stop) return;
+    extern __shared__ double smem[];
+    __shared__ double red[32];
+    const Consts& K = a.K;
+    Gs3Div D;
+    D.dx2 = make_invdiv3(K.dx2); D.dy2 = make_invdiv3(K.dy2); D.apd = make_invdiv3(K.ap_d);
+    double acc[H];
+#pragma unroll
+    for (int t = 0; t < H; ++t) acc[t] = 0.0;
+    jtb_pass<H>(a, a.Var + (long long)a.k * K.plane, a.scratch, nsw, smem, acc, D, res_r0, res_r1);
+#pragma unroll
+    for (int t = 0; t < H; ++t) {
+        const double tot = block_sum(acc[t], red);
+        if (threadIdx.x == 0) ja.partials[(size_t)t * gridDim.x + blockIdx.x] = tot;
+    }
+}
+// sums[t] = sum over CTAs in index order
+__global__ void k_jacobi_tb_sums(JtbArgs ja, int nparts, int nsw, double* __restrict__ sums) {
+    if (ja.s.ctrl->stop) return;
+    if ((int)threadIdx.x < nsw) {
+        double s = 0.0;
+        for (int b = 0; b < nparts; ++b) s += ja.partials[(size_t)threadIdx.x * nparts + b];
+        sums[threadIdx.x] = s;
+    }
+}
+// accept a pass: the interior of the scratch plane becomes the plane
+__global__ void k_jacobi_tb_commit(SolveArgs a) {
+    if (a.ctrl->stop) return;
+    const Consts& K = a.K;
+    double* A = a.Var + (long long)a.k * K.plane;
+    const long long ncell = (long long)K.nx * K.ny;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < ncell; idx += (long long)gridDim.x * blockDim.x) {
+        const long long c = (idx / K.ny + 1) * K.pitch + (idx % K.ny) + 1;
+        A[c] = a.scratch[c];
     }
 }
 

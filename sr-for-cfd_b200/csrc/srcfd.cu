@@ -86,6 +86,8 @@ struct srcfd_handle {
     size_t jtb_smem = 0;
     const void* jtb_fn = nullptr;
     double* jtb_partials = nullptr;
+    double* jtb_sums = nullptr;         // [8] per-sweep residual sums of the last single pass (device)
+    const void* jtb_pass_fn = nullptr;
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
@@ -249,6 +251,8 @@ static int plan_jtb(srcfd_handle* h) {
     if (const char* e = getenv("SRCFD_JTB_H")) H = atoi(e) == 4 ? 4 : 8;
     h->jtb_fn = H == 4 ? (const void*)k_jacobi_tb<4> : (const void*)k_jacobi_tb<8>;
     h->jtb_smem = H == 4 ? JtbShape<4>::smem : JtbShape<8>::smem;
+    h->jtb_pass_fn = H == 4 ? (const void*)k_jacobi_tb_pass<4> : (const void*)k_jacobi_tb_pass<8>;
+    if (int rc = raise_smem_limit(h->dev, h->jtb_pass_fn, h->jtb_smem)) return rc;
     if (int rc = raise_smem_limit(h->dev, h->jtb_fn, h->jtb_smem)) return rc;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->jtb_fn, JTB_THREADS, h->jtb_smem));
@@ -310,7 +314,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
-    cudaFree(h->jtb_partials);
+    cudaFree(h->jtb_partials); cudaFree(h->jtb_sums);
     cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
     cudaFree(h->sweeps1); cudaFree(h->sweeps2);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
@@ -371,7 +375,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
-    if (h->jtb_H) CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1)));
+    if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8)); }
     if (h->gs3) {
         const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
         CKB(cudaMalloc(&h->gs3_ll, llb));
@@ -810,6 +814,54 @@ int srcfd_k_solve_pressure(srcfd_handle* h, int32_t* sweeps, double* last_rms) {
     TRY(l_pressure_rhs(h));
     TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
     return finish_inner(h, 2, sweeps, last_rms);
+}
+int srcfd_jacobi_pass_max(srcfd_handle* h, int* H) {
+    CKH(h);
+    if (!H) return fail(SRCFD_ERR_ARG, "null H");
+    *H = h->jtb_H;
+    return SRCFD_OK;
+}
+int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, double* sums) {
+    CKH(h);
+    if (!h->jtb_H) return fail(SRCFD_ERR_ARG, "the temporally blocked Jacobi kernel is disabled (SRCFD_JTB=0)");
+    if (nsweeps < 1 || nsweeps > h->jtb_H) return fail(SRCFD_ERR_ARG, "nsweeps must be 1..srcfd_jacobi_pass_max()");
+    if (own_row0 < 1 || own_row1 > h->p.nx || own_row0 > own_row1) return fail(SRCFD_ERR_ARG, "bad row range");
+    if (!sums) return fail(SRCFD_ERR_ARG, "null sums");
+    if (recompute_rhs) TRY(l_pressure_rhs(h));
+    JtbArgs ja;
+    SolveArgs& a = ja.s;
+    a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
+    a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
+    a.k = 2; a.slot = 2; a.tol = 0.0; a.max_iter = nsweeps;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
+    ja.partials = h->jtb_partials;
+    // ghost cells of the scratch plane must match the plane (the pass only writes interior cells)
+    CK(cudaMemcpyAsync(h->scratch, h->Var + 2 * (size_t)h->K.plane, sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
+    void* args[] = {&ja, &nsweeps, &own_row0, &own_row1};
+    CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
+    k_jacobi_tb_sums<<<1, 32, 0, h->stream>>>(ja, h->jtb_grid, nsweeps, h->jtb_sums);
+    LAUNCH_CHECK(h);
+    h->launches += 2;
+    if (commit) {
+        k_jacobi_tb_commit<<<std::max(1, h->tail_blocks / 4), 256, 0, h->stream>>>(a);
+        LAUNCH_CHECK(h);
+        h->launches += 1;
+    }
+    CK(cudaMemcpyAsync(sums, h->jtb_sums, sizeof(double) * nsweeps, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SRCFD_OK;
+}
+int srcfd_k_jacobi_commit(srcfd_handle* h) {
+    CKH(h);
+    SolveArgs a;
+    a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
+    a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
+    a.k = 2; a.slot = 2; a.tol = 0.0; a.max_iter = 0;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
+    k_jacobi_tb_commit<<<std::max(1, h->tail_blocks / 4), 256, 0, h->stream>>>(a);
+    LAUNCH_CHECK(h);
+    h->launches += 1;
+    return SRCFD_OK;
 }
 int srcfd_k_solve_momentum(srcfd_handle* h, int k, int scheme, int32_t* sweeps, double* last_rms) {
     CKH(h);

@@ -1,0 +1,71 @@
+"""Slab decomposition on the GPU back-end: the single-pass C-ABI entry (srcfd_k_jacobi_pass / _commit) driven by
+srcfd.slab on two slabs of one device (threads stand in for ranks, host copies for NVLink), against the single-domain
+oracle in Jacobi order.  The NCCL path itself is exercised by tools/slab_bench.py on a multi-GPU box."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Pair:
+    """Two GpuSlab objects in one process: exchange and all-reduce through host memory, in lock step."""
+
+    def __init__(self, slabs):
+        self.slabs = slabs
+        self.bar = threading.Barrier(len(slabs))
+        self.box = [None] * len(slabs)
+
+    def exchange(self, r):
+        s = self.slabs[r]; P = s.part
+        nxl = P.nx_local
+        V = np.zeros((3, nxl + 2, s.ny + 2)); s.h.download(Var=V)
+        self.box[r] = V[2].copy()
+        self.bar.wait()
+        if P.lo:
+            up = self.slabs[r - 1]; U = self.box[r - 1]
+            V[2, 1:1 + P.halo] = U[up.part.local_own1 - P.halo + 1:up.part.local_own1 + 1]
+        if P.hi:
+            dn = self.slabs[r + 1]; D = self.box[r + 1]
+            V[2, P.local_own1 + 1:P.local_own1 + 1 + P.halo] = D[dn.part.local_own0:dn.part.local_own0 + P.halo]
+        self.bar.wait()
+        s.h.upload(Var=V)
+
+    def allreduce(self, r, v):
+        self.box[r] = np.array(v, dtype=np.float64)
+        self.bar.wait()
+        tot = sum(self.box[i] for i in range(len(self.slabs)))
+        self.bar.wait()
+        return tot
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_slab_jacobi_on_gpu_matches_oracle(world):
+    from srcfd.slab import GpuSlab, slab_jacobi_solve
+    nx, ny = 96, 70
+    rng = np.random.default_rng(1)
+    Var = rng.uniform(-1, 1, (3, nx + 2, ny + 2)); Ff = 0.05 * rng.uniform(-1, 1, (4, nx + 2, ny + 2))
+    dx, dy, dt, rho = 1.0 / nx, 1.0 / ny, 1e-3, 1.0
+    for tol, cap in ((0.0, 19), (30.0, 200), (1e-30, 8)):
+        slabs = [GpuSlab(nx, ny, dx, dy, dt, rho, Var, Ff, world, r, device=0) for r in range(world)]
+        pair = _Pair(slabs)
+        res = [None] * world
+
+        def run(r):
+            s = slabs[r]
+            res[r] = slab_jacobi_solve(s.part if world > 1 else type(s.part)(nx, 1, 0, s.H), nx * ny, tol, cap, s.run_pass, s.commit,
+                                       lambda: pair.exchange(r), lambda v: pair.allreduce(r, v))
+
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in th: t.start()
+        for t in th: t.join(timeout=120)
+        assert all(x is not None for x in res)
+        rows = np.concatenate([s.owned_rows() for s in slabs], axis=0)
+        B = Var.copy()
+        m = O.solve_pressure(B, Ff, nx, ny, dx, dy, dt, rho, dx * dy, order=O.ORDER_JACOBI, tolerance=tol, max_iter=cap)
+        assert all(n == m for n, _ in res), (world, tol, cap, res, m)
+        assert np.array_equal(rows, B[2, 1:-1]), (world, tol, cap, np.max(np.abs(rows - B[2, 1:-1])))
+        for s in slabs: s.h.close()
