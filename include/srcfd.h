@@ -123,6 +123,9 @@ int srcfd_k_solve_pressure(srcfd_handle *h, int32_t *sweeps, double *last_rms); 
 int srcfd_jacobi_pass_max(srcfd_handle *h, int *H);
 int srcfd_k_jacobi_pass(srcfd_handle *h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, double *sums);
 int srcfd_k_jacobi_commit(srcfd_handle *h);
+/* Device address of the 8 per-sweep sums of the last pass (sums == NULL above skips the host copy and the stream
+ * synchronisation, so a multi-GPU caller can all-reduce them in place). */
+int srcfd_jacobi_sums_ptr(srcfd_handle *h, uint64_t *ptr);
 int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, double *last_rms); /* LDC.py:248-290 */
 /* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
 int srcfd_k_implicit_solve(srcfd_handle *h);

@@ -254,6 +254,15 @@ __global__ void k_jacobi_tb_sums(JtbArgs ja, int nparts, int nsw, double* __rest
         sums[threadIdx.x] = s;
     }
 }
+// boundary cells of the plane -> scratch plane (a pass writes interior cells only)
+__global__ void k_jacobi_tb_ghosts(SolveArgs a) {
+    if (a.ctrl->stop) return;
+    const Consts& K = a.K;
+    const double* A = a.Var + (long long)a.k * K.plane;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= K.ny + 1) { a.scratch[t] = A[t]; a.scratch[(long long)(K.nx + 1) * K.pitch + t] = A[(long long)(K.nx + 1) * K.pitch + t]; }
+    if (t <= K.nx + 1) { a.scratch[(long long)t * K.pitch] = A[(long long)t * K.pitch]; a.scratch[(long long)t * K.pitch + K.ny + 1] = A[(long long)t * K.pitch + K.ny + 1]; }
+}
 // accept a pass: the interior of the scratch plane becomes the plane
 __global__ void k_jacobi_tb_commit(SolveArgs a) {
     if (a.ctrl->stop) return;

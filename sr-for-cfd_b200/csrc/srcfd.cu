@@ -826,7 +826,6 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     if (!h->jtb_H) return fail(SRCFD_ERR_ARG, "the temporally blocked Jacobi kernel is disabled (SRCFD_JTB=0)");
     if (nsweeps < 1 || nsweeps > h->jtb_H) return fail(SRCFD_ERR_ARG, "nsweeps must be 1..srcfd_jacobi_pass_max()");
     if (own_row0 < 1 || own_row1 > h->p.nx || own_row0 > own_row1) return fail(SRCFD_ERR_ARG, "bad row range");
-    if (!sums) return fail(SRCFD_ERR_ARG, "null sums");
     if (recompute_rhs) TRY(l_pressure_rhs(h));
     JtbArgs ja;
     SolveArgs& a = ja.s;
@@ -835,8 +834,9 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     a.k = 2; a.slot = 2; a.tol = 0.0; a.max_iter = nsweeps;
     a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
     ja.partials = h->jtb_partials;
-    // ghost cells of the scratch plane must match the plane (the pass only writes interior cells)
-    CK(cudaMemcpyAsync(h->scratch, h->Var + 2 * (size_t)h->K.plane, sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
+    // boundary cells of the scratch plane must match the plane (the pass only writes interior cells)
+    k_jacobi_tb_ghosts<<<(std::max(h->K.nx, h->K.ny) + 2 + 127) / 128, 128, 0, h->stream>>>(a);
+    LAUNCH_CHECK(h);
     void* args[] = {&ja, &nsweeps, &own_row0, &own_row1};
     CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
     k_jacobi_tb_sums<<<1, 32, 0, h->stream>>>(ja, h->jtb_grid, nsweeps, h->jtb_sums);
@@ -847,8 +847,16 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
         LAUNCH_CHECK(h);
         h->launches += 1;
     }
-    CK(cudaMemcpyAsync(sums, h->jtb_sums, sizeof(double) * nsweeps, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (sums) {                                             // NULL: the caller reduces the device copy (srcfd_jacobi_sums_ptr)
+        CK(cudaMemcpyAsync(sums, h->jtb_sums, sizeof(double) * nsweeps, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return SRCFD_OK;
+}
+int srcfd_jacobi_sums_ptr(srcfd_handle* h, uint64_t* ptr) {
+    CKH(h);
+    if (!ptr) return fail(SRCFD_ERR_ARG, "null ptr");
+    *ptr = (uint64_t)(uintptr_t)h->jtb_sums;
     return SRCFD_OK;
 }
 int srcfd_k_jacobi_commit(srcfd_handle* h) {

@@ -3,10 +3,10 @@
 Scope: the JACOBI-order pressure solve (the order BASELINE's north star names for the decomposed grid), i.e.
 solve_pressure (PyCFD_ML_accelerated.py:292-314) with every cell of a sweep computed from the previous iterate.  One
 process per GPU; rank r owns a contiguous block of interior rows.  The temporally blocked kernel advances H sweeps per
-pass, so a slab carries H halo rows on each side that has a neighbour and exchanges them ONCE per pass (H sweeps), not
-per sweep: after H sweeps stale information from beyond the halo has travelled H rows and has not reached an owned row.
-Per pass: halo exchange (NCCL send/recv of H contiguous rows each way), one kernel pass, one all-reduce of the H
-per-sweep residual sums.  The break rule ("stop after the first sweep with rms < tol", LDC.py:310-313) is applied to the
+pass; a slab carries M*H halo rows on each side that has a neighbour and exchanges them once per M passes (M*H sweeps),
+not per sweep: stale information from beyond the halo travels one row per sweep, so after M*H sweeps it has not reached
+an owned row.  Per pass: one kernel pass and one all-reduce of the H per-sweep residual sums (in place on the device);
+per M passes: one halo exchange (NCCL send/recv of M*H contiguous rows each way).  The break rule ("stop after the first sweep with rms < tol", LDC.py:310-313) is applied to the
 globally reduced sums BEFORE a pass is committed; if an earlier sweep of the pass met the tolerance the pass is
 repeated with fewer sweeps, so the result is the single-domain Jacobi result bit for bit.
 
@@ -65,14 +65,21 @@ class SlabPartition:
 
 def slab_jacobi_solve(part: SlabPartition, ncells_global: int, tol: float, max_iter: int,
                       run_pass: Callable[[int, bool], np.ndarray], commit: Callable[[], None],
-                      exchange: Callable[[], None], allreduce_sum: Callable[[np.ndarray], np.ndarray]) -> Tuple[int, float]:
+                      exchange: Callable[[], None], allreduce_sum: Callable[[np.ndarray], np.ndarray],
+                      sweeps_per_pass: Optional[int] = None) -> Tuple[int, float]:
     """The loop every rank runs.  run_pass(nsw, commit_now) -> per-sweep sums of R^2 over the OWNED rows (length nsw);
-    exchange() refreshes the halo rows from the neighbours' owned rows; returns (sweeps, last rms)."""
-    H = part.halo if part.world > 1 else max(1, part.halo)
+    exchange() refreshes the halo rows from the neighbours' owned rows; returns (sweeps, last rms).
+    sweeps_per_pass (H) may be smaller than the halo depth: the halos are then exchanged every halo // H passes (stale
+    data advances one row per sweep, so halo rows of depth M*H protect the owned rows for M passes)."""
+    H = sweeps_per_pass or (part.halo if part.world > 1 else max(1, part.halo))
+    budget = 0                                               # sweeps the current halo contents are still good for
     n, rms_last = 0, 0.0
     while n < max_iter:
         nsw = min(H, max_iter - n)
-        exchange()
+        if part.world > 1 and budget < nsw:
+            exchange()
+            budget = part.halo
+        budget -= nsw
         sums = allreduce_sum(np.asarray(run_pass(nsw, False), dtype=np.float64))
         rms = np.sqrt(sums / float(ncells_global))
         hit = np.nonzero(rms < tol)[0]
@@ -105,11 +112,14 @@ class GpuSlab:
     loads the same ones; only the local rows are uploaded)."""
 
     def __init__(self, nx: int, ny: int, dx: float, dy: float, dt: float, rho: float, Var_global: np.ndarray,
-                 Ff_global: np.ndarray, world: int, rank: int, device: int = 0, halo: Optional[int] = None):
+                 Ff_global: np.ndarray, world: int, rank: int, device: int = 0, halo: Optional[int] = None,
+                 passes_per_exchange: int = 4):
         from . import _capi as capi
         self.capi = capi
         # the halo depth is the number of sweeps per pass of the kernel for a grid of the LOCAL size
-        probe = halo if halo is not None else (4 if (nx // world) * ny >= (1 << 20) else 8)
+        H_guess = 4 if (nx // world) * ny >= (1 << 20) else 8
+        probe = halo if halo is not None else H_guess * max(1, passes_per_exchange)
+        probe = max(1, min(probe, nx // world))             # a slab cannot be thinner than its halo
         self.part = SlabPartition(nx, world, rank, probe if world > 1 else 0)
         p = capi.Params()
         p.nx, p.ny = self.part.nx_local, ny
@@ -120,9 +130,7 @@ class GpuSlab:
                 p.bc_types[k][s] = 1 if k == 2 else 0
         self.h = capi.Handle(p)
         self.H = self.h.jacobi_pass_max()
-        if world > 1 and self.H < self.part.halo:
-            raise RuntimeError(f"kernel advances {self.H} sweeps per pass, halo is {self.part.halo}")
-        self.nsw_max = self.part.halo if world > 1 else self.H
+        self.nsw_max = min(self.H, self.part.halo) if world > 1 else self.H      # sweeps per kernel pass
         self.ny, self.pitch = ny, ny + 2
         self.ncells_global = nx * ny
         g0, g1 = self.part.global_rows()
@@ -130,18 +138,28 @@ class GpuSlab:
         self._rhs_done = False
         ptrs = self.h.device_ptrs()
         self.p_ptr = ptrs[0] + 2 * (self.part.nx_local + 2) * self.pitch * 8       # plane k = 2
-        self._views = None
+        self._sums = None
 
     # rows as torch tensors aliasing the library's memory
     def _rows(self, first_row: int, nrows: int):
         import torch
         return torch.as_tensor(_DevRows(self.p_ptr + first_row * self.pitch * 8, nrows, self.pitch), device=f"cuda:{self.h.params.device}")
 
-    def run_pass(self, nsw: int, commit_now: bool) -> np.ndarray:
-        sums = self.h.k_jacobi_pass(nsw, self.part.local_own0, self.part.local_own1, recompute_rhs=not self._rhs_done,
+    def run_pass(self, nsw: int, commit_now: bool):
+        """Enqueue one pass; the per-sweep sums stay on the device (all-reduced in place by allreduce_sum)."""
+        self.h.k_jacobi_pass_device(nsw, self.part.local_own0, self.part.local_own1, recompute_rhs=not self._rhs_done,
                                     commit=commit_now)
         self._rhs_done = True
-        return sums
+        self._nsw = nsw
+        return np.zeros(nsw)                                 # placeholder: the values live at jacobi_sums_ptr
+
+    def read_sums(self, n: int) -> np.ndarray:
+        """Per-sweep sums of the last pass (this slab's owned rows), copied to the host."""
+        import torch
+        if self._sums is None:
+            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 1, 8), device=f"cuda:{self.h.params.device}")[0]
+        self.h.synchronize()
+        return self._sums[:n].cpu().numpy()
 
     def commit(self):
         self.h.k_jacobi_commit()
@@ -167,16 +185,17 @@ class GpuSlab:
 
     def allreduce_sum(self, v: np.ndarray) -> np.ndarray:
         import torch, torch.distributed as dist
-        if self.part.world == 1:
-            return v
-        t = torch.from_numpy(v.copy()).to(f"cuda:{self.h.params.device}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t.cpu().numpy()
+        if self._sums is None:
+            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 1, 8), device=f"cuda:{self.h.params.device}")[0]
+        self.h.synchronize()                                 # the pass ran on the library's stream
+        if self.part.world > 1:
+            dist.all_reduce(self._sums, op=dist.ReduceOp.SUM)
+        return self._sums[: len(v)].cpu().numpy()
 
     def solve(self, tol: float = 1e-6, max_iter: int = 1000) -> Tuple[int, float]:
         part = self.part if self.part.world > 1 else SlabPartition(self.part.nx, 1, 0, self.H)
         return slab_jacobi_solve(part, self.ncells_global, tol, max_iter, self.run_pass, self.commit, self.exchange,
-                                 self.allreduce_sum)
+                                 self.allreduce_sum, sweeps_per_pass=self.nsw_max)
 
     def owned_rows(self) -> np.ndarray:
         """(n_own, ny+2) owned rows of the pressure plane."""

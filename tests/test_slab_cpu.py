@@ -88,9 +88,10 @@ def _worker(rank, world, port, q):
     dx, dy, dt, rho = 1.0 / nx, 1.0 / ny, 1e-3, 1.0
     out = []
     for tol, cap in ((0.0, 10), (0.0, 3), (30.0, 40), (24.0, 60), (1e-30, 9)):      # caps off the pass size, stops inside a pass
-        part = SlabPartition(nx, world, rank, H)
+        halo = H if cap % 2 else 2 * H                   # also: halos twice as deep as a pass, exchanged every second pass
+        part = SlabPartition(nx, world, rank, halo)
         be = _NumpySlab(part, Var, Ff, ny, dx, dy, dt, rho, dist)
-        n, rms = slab_jacobi_solve(part, nx * ny, tol, cap, be.run_pass, be.commit, be.exchange, be.allreduce)
+        n, rms = slab_jacobi_solve(part, nx * ny, tol, cap, be.run_pass, be.commit, be.exchange, be.allreduce, sweeps_per_pass=H)
         own = be.Var[2, part.local_own0:part.local_own1 + 1]
         gathered = [None] * world
         dist.all_gather_object(gathered, own)
