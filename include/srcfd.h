@@ -121,11 +121,14 @@ int srcfd_k_solve_pressure(srcfd_handle *h, int32_t *sweeps, double *last_rms); 
  * the scratch plane) so that the caller can apply the break rule to the globally reduced sums first: accept with
  * srcfd_k_jacobi_commit, or repeat the pass with fewer sweeps. */
 int srcfd_jacobi_pass_max(srcfd_handle *h, int *H);
-int srcfd_k_jacobi_pass(srcfd_handle *h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, double *sums);
+int srcfd_k_jacobi_pass(srcfd_handle *h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, int slot,
+                        double *sums);
 int srcfd_k_jacobi_commit(srcfd_handle *h);
-/* Device address of the 8 per-sweep sums of the last pass (sums == NULL above skips the host copy and the stream
- * synchronisation, so a multi-GPU caller can all-reduce them in place). */
+/* Device address of the per-sweep sums, [16 slots][8]: a pass writes slot `slot` (sums == NULL above skips the host copy
+ * and the stream synchronisation, so a multi-GPU caller can run a block of passes and all-reduce all their sums at once).
+ * srcfd_k_jacobi_snapshot saves (restore = 0) / restores (1) the whole pressure plane, for rolling such a block back. */
 int srcfd_jacobi_sums_ptr(srcfd_handle *h, uint64_t *ptr);
+int srcfd_k_jacobi_snapshot(srcfd_handle *h, int restore);
 int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, double *last_rms); /* LDC.py:248-290 */
 /* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
 int srcfd_k_implicit_solve(srcfd_handle *h);

@@ -375,7 +375,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
-    if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8)); }
+    if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream)); }
     if (h->gs3) {
         const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
         CKB(cudaMalloc(&h->gs3_ll, llb));
@@ -821,11 +821,13 @@ int srcfd_jacobi_pass_max(srcfd_handle* h, int* H) {
     *H = h->jtb_H;
     return SRCFD_OK;
 }
-int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, double* sums) {
+int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, int slot,
+                        double* sums) {
     CKH(h);
     if (!h->jtb_H) return fail(SRCFD_ERR_ARG, "the temporally blocked Jacobi kernel is disabled (SRCFD_JTB=0)");
     if (nsweeps < 1 || nsweeps > h->jtb_H) return fail(SRCFD_ERR_ARG, "nsweeps must be 1..srcfd_jacobi_pass_max()");
     if (own_row0 < 1 || own_row1 > h->p.nx || own_row0 > own_row1) return fail(SRCFD_ERR_ARG, "bad row range");
+    if (slot < 0 || slot >= 16) return fail(SRCFD_ERR_ARG, "slot must be 0..15");
     if (recompute_rhs) TRY(l_pressure_rhs(h));
     JtbArgs ja;
     SolveArgs& a = ja.s;
@@ -839,7 +841,7 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     LAUNCH_CHECK(h);
     void* args[] = {&ja, &nsweeps, &own_row0, &own_row1};
     CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
-    k_jacobi_tb_sums<<<1, 32, 0, h->stream>>>(ja, h->jtb_grid, nsweeps, h->jtb_sums);
+    k_jacobi_tb_sums<<<1, 32, 0, h->stream>>>(ja, h->jtb_grid, nsweeps, h->jtb_sums + 8 * slot);
     LAUNCH_CHECK(h);
     h->launches += 2;
     if (commit) {
@@ -848,9 +850,17 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
         h->launches += 1;
     }
     if (sums) {                                             // NULL: the caller reduces the device copy (srcfd_jacobi_sums_ptr)
-        CK(cudaMemcpyAsync(sums, h->jtb_sums, sizeof(double) * nsweeps, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(sums, h->jtb_sums + 8 * slot, sizeof(double) * nsweeps, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return SRCFD_OK;
+}
+// whole pressure plane (halos and ghosts included) <-> the snapshot buffer: speculative blocks of passes roll back with it
+int srcfd_k_jacobi_snapshot(srcfd_handle* h, int restore) {
+    CKH(h);
+    double* p = h->Var + 2 * (size_t)h->K.plane;
+    if (restore) CK(cudaMemcpyAsync(p, h->scratch2, sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemcpyAsync(h->scratch2, p, sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
     return SRCFD_OK;
 }
 int srcfd_jacobi_sums_ptr(srcfd_handle* h, uint64_t* ptr) {

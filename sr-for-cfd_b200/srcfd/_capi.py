@@ -56,7 +56,7 @@ SYMBOLS = [
     "srcfd_reset_counters", "srcfd_solve", "srcfd_k_copy_new_to_old", "srcfd_k_apply_bc",
     "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
-    "srcfd_k_solve_pressure", "srcfd_jacobi_pass_max", "srcfd_k_jacobi_pass", "srcfd_k_jacobi_commit", "srcfd_jacobi_sums_ptr", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
+    "srcfd_k_solve_pressure", "srcfd_jacobi_pass_max", "srcfd_k_jacobi_pass", "srcfd_k_jacobi_commit", "srcfd_jacobi_sums_ptr", "srcfd_k_jacobi_snapshot", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
     "srcfd_sr_last_error", "srcfd_sr_create", "srcfd_sr_destroy", "srcfd_sr_set_encoder", "srcfd_sr_set_decoder",
     "srcfd_sr_encode", "srcfd_sr_decode", "srcfd_sr_predict", "srcfd_sr_decode_device", "srcfd_sr_launch_count",
@@ -253,14 +253,17 @@ class Handle:
         commit=False leaves the plane untouched until k_jacobi_commit()."""
         sums = np.zeros(nsweeps)
         check(lib().srcfd_k_jacobi_pass(self._h, C.c_int(nsweeps), C.c_int(own_row0), C.c_int(own_row1),
-                                        C.c_int(int(recompute_rhs)), C.c_int(int(commit)), _ptr(sums)))
+                                        C.c_int(int(recompute_rhs)), C.c_int(int(commit)), C.c_int(0), _ptr(sums)))
         return sums
 
     def k_jacobi_pass_device(self, nsweeps: int, own_row0: int, own_row1: int, recompute_rhs: bool = False,
-                             commit: bool = False):
-        """Same, but the sums stay on the device (jacobi_sums_ptr) and the call does not synchronise."""
+                             commit: bool = False, slot: int = 0):
+        """Same, but the sums stay on the device (slot `slot` of jacobi_sums_ptr) and the call does not synchronise."""
         check(lib().srcfd_k_jacobi_pass(self._h, C.c_int(nsweeps), C.c_int(own_row0), C.c_int(own_row1),
-                                        C.c_int(int(recompute_rhs)), C.c_int(int(commit)), None))
+                                        C.c_int(int(recompute_rhs)), C.c_int(int(commit)), C.c_int(slot), None))
+
+    def k_jacobi_snapshot(self, restore: bool = False):
+        check(lib().srcfd_k_jacobi_snapshot(self._h, C.c_int(int(restore))))
 
     def jacobi_sums_ptr(self) -> int:
         p = C.c_uint64(0)

@@ -96,6 +96,48 @@ def slab_jacobi_solve(part: SlabPartition, ncells_global: int, tol: float, max_i
     return n, rms_last
 
 
+def slab_jacobi_solve_blocks(part: SlabPartition, ncells_global: int, tol: float, max_iter: int, be, H: int, M: int
+                             ) -> Tuple[int, float]:
+    """Same result, fewer synchronisations: blocks of up to M passes (H sweeps each) run back to back and commit as
+    they go; their M*H residual sums are reduced over the ranks ONCE per block.  A block is speculative: the plane
+    (halos included) is saved first, and if some sweep inside the block met the tolerance the block is rolled back and
+    replayed up to exactly that sweep.  Needs halos of depth >= M*H.  Back-end `be`: exchange(), snapshot(), restore(),
+    run_pass(nsw, slot) (commits), reduce(nslots) -> (nslots, >=H) globally summed per-sweep sums of R^2."""
+    if part.world > 1 and part.halo < M * H:
+        raise ValueError(f"halo depth {part.halo} < {M} passes x {H} sweeps")
+    n, rms_last = 0, 0.0
+    while n < max_iter:
+        plan, rem = [], max_iter - n
+        while rem > 0 and len(plan) < M:
+            plan.append(min(H, rem)); rem -= plan[-1]
+        if part.world > 1:
+            be.exchange()
+        be.snapshot()
+        for m, nsw in enumerate(plan):
+            be.run_pass(nsw, m)
+        S = be.reduce(len(plan))
+        hit = None
+        for m, nsw in enumerate(plan):
+            r = np.sqrt(S[m, :nsw] / float(ncells_global))
+            idx = np.nonzero(r < tol)[0]
+            if idx.size:
+                hit = (m, int(idx[0]), float(r[idx[0]]))
+                break
+        if hit is None:
+            n += sum(plan)
+            rms_last = float(np.sqrt(S[len(plan) - 1, plan[-1] - 1] / float(ncells_global)))
+            continue
+        m_, t_, r_ = hit
+        total = n + sum(plan[:m_]) + t_ + 1
+        if not (m_ == len(plan) - 1 and t_ == plan[-1] - 1):       # overshoot: roll back, replay up to that sweep
+            be.restore()
+            for m in range(m_):
+                be.run_pass(plan[m], m)
+            be.run_pass(t_ + 1, m_)
+        return total, r_
+    return n, rms_last
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU back-end: one libsrcfd handle per rank on the local grid, torch.distributed for halos and the all-reduce
 # ---------------------------------------------------------------------------------------------------------------------
@@ -145,21 +187,42 @@ class GpuSlab:
         import torch
         return torch.as_tensor(_DevRows(self.p_ptr + first_row * self.pitch * 8, nrows, self.pitch), device=f"cuda:{self.h.params.device}")
 
-    def run_pass(self, nsw: int, commit_now: bool):
-        """Enqueue one pass; the per-sweep sums stay on the device (all-reduced in place by allreduce_sum)."""
+    def run_pass(self, nsw: int, commit_now, slot: Optional[int] = None):
+        """Enqueue one pass; the per-sweep sums stay on the device (slot `slot` of jacobi_sums_ptr).  Two calling
+        conventions: run_pass(nsw, commit_now) for slab_jacobi_solve, run_pass(nsw, slot) (always commits) for the
+        block driver."""
+        if slot is None and not isinstance(commit_now, bool):
+            slot, commit_now = int(commit_now), True
         self.h.k_jacobi_pass_device(nsw, self.part.local_own0, self.part.local_own1, recompute_rhs=not self._rhs_done,
-                                    commit=commit_now)
+                                    commit=bool(commit_now), slot=slot or 0)
         self._rhs_done = True
-        self._nsw = nsw
         return np.zeros(nsw)                                 # placeholder: the values live at jacobi_sums_ptr
+
+    def snapshot(self):
+        self.h.k_jacobi_snapshot(False)
+
+    def restore(self):
+        self.h.k_jacobi_snapshot(True)
+
+    def _sums_tensor(self):
+        import torch
+        if self._sums is None:
+            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 16, 8), device=f"cuda:{self.h.params.device}")
+        return self._sums
+
+    def reduce(self, nslots: int) -> np.ndarray:
+        """(nslots, 8) per-sweep sums of the last block, summed over the ranks (one collective, one synchronisation)."""
+        import torch.distributed as dist
+        t = self._sums_tensor()
+        self.h.synchronize()
+        if self.part.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t[:nslots].cpu().numpy()
 
     def read_sums(self, n: int) -> np.ndarray:
         """Per-sweep sums of the last pass (this slab's owned rows), copied to the host."""
-        import torch
-        if self._sums is None:
-            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 1, 8), device=f"cuda:{self.h.params.device}")[0]
         self.h.synchronize()
-        return self._sums[:n].cpu().numpy()
+        return self._sums_tensor()[0, :n].cpu().numpy()
 
     def commit(self):
         self.h.k_jacobi_commit()
@@ -185,17 +248,16 @@ class GpuSlab:
 
     def allreduce_sum(self, v: np.ndarray) -> np.ndarray:
         import torch, torch.distributed as dist
-        if self._sums is None:
-            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 1, 8), device=f"cuda:{self.h.params.device}")[0]
+        t = self._sums_tensor()[0]
         self.h.synchronize()                                 # the pass ran on the library's stream
         if self.part.world > 1:
-            dist.all_reduce(self._sums, op=dist.ReduceOp.SUM)
-        return self._sums[: len(v)].cpu().numpy()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t[: len(v)].cpu().numpy()
 
     def solve(self, tol: float = 1e-6, max_iter: int = 1000) -> Tuple[int, float]:
         part = self.part if self.part.world > 1 else SlabPartition(self.part.nx, 1, 0, self.H)
-        return slab_jacobi_solve(part, self.ncells_global, tol, max_iter, self.run_pass, self.commit, self.exchange,
-                                 self.allreduce_sum, sweeps_per_pass=self.nsw_max)
+        M = max(1, min(16, part.halo // self.nsw_max)) if self.part.world > 1 else 8
+        return slab_jacobi_solve_blocks(part, self.ncells_global, tol, max_iter, self, self.nsw_max, M)
 
     def owned_rows(self) -> np.ndarray:
         """(n_own, ny+2) owned rows of the pressure plane."""

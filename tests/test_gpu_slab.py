@@ -64,6 +64,11 @@ def test_slab_jacobi_on_gpu_matches_oracle(world):
         for t in th: t.join(timeout=120)
         assert all(x is not None for x in res)
         rows = np.concatenate([s.owned_rows() for s in slabs], axis=0)
+        if world == 1:                                      # the block driver GpuSlab.solve() uses (no communication needed here)
+            s1 = GpuSlab(nx, ny, dx, dy, dt, rho, Var, Ff, 1, 0, device=0)
+            n1, _ = s1.solve(tol, cap)
+            assert n1 == res[0][0] and np.array_equal(s1.owned_rows(), rows)
+            s1.h.close()
         B = Var.copy()
         m = O.solve_pressure(B, Ff, nx, ny, dx, dy, dt, rho, dx * dy, order=O.ORDER_JACOBI, tolerance=tol, max_iter=cap)
         assert all(n == m for n, _ in res), (world, tol, cap, res, m)

@@ -9,7 +9,7 @@ import pytest
 import torch.multiprocessing as mp
 
 from oracle import oracle as O
-from srcfd.slab import SlabPartition, slab_jacobi_solve
+from srcfd.slab import SlabPartition, slab_jacobi_solve, slab_jacobi_solve_blocks
 
 
 def test_partition_covers_rows_once():
@@ -33,6 +33,7 @@ class _NumpySlab:
         g0, g1 = part.global_rows()
         self.Var = np.ascontiguousarray(Var[:, g0:g1 + 1]); self.Ff = np.ascontiguousarray(Ff[:, g0:g1 + 1])
         self.pending = None
+        self.slots = np.zeros((16, 8))
 
     def _sweeps(self, nsw):
         V = self.Var.copy()
@@ -57,6 +58,16 @@ class _NumpySlab:
 
     def commit(self):
         self.Var = self.pending
+
+    # back-end interface of the block driver
+    def snapshot(self): self.saved = self.Var.copy()
+    def restore(self): self.Var = self.saved.copy()
+    def run_pass_slot(self, nsw, slot):
+        self.Var, sums = self._sweeps(nsw)
+        self.slots[slot, :nsw] = sums
+    def reduce(self, nslots):
+        import torch
+        t = torch.from_numpy(self.slots.copy()); self.dist.all_reduce(t); return t.numpy()[:nslots]
 
     def exchange(self):
         import torch
@@ -92,6 +103,12 @@ def _worker(rank, world, port, q):
         part = SlabPartition(nx, world, rank, halo)
         be = _NumpySlab(part, Var, Ff, ny, dx, dy, dt, rho, dist)
         n, rms = slab_jacobi_solve(part, nx * ny, tol, cap, be.run_pass, be.commit, be.exchange, be.allreduce, sweeps_per_pass=H)
+        # the same problem through the speculative block driver (M = 2 passes per exchange / reduction)
+        part2 = SlabPartition(nx, world, rank, 2 * H)
+        be2 = _NumpySlab(part2, Var, Ff, ny, dx, dy, dt, rho, dist)
+        be2.run_pass = be2.run_pass_slot
+        n2, rms2 = slab_jacobi_solve_blocks(part2, nx * ny, tol, cap, be2, H, 2)
+        assert n2 == n and np.array_equal(be2.Var[2, part2.local_own0:part2.local_own1 + 1], be.Var[2, part.local_own0:part.local_own1 + 1])
         own = be.Var[2, part.local_own0:part.local_own1 + 1]
         gathered = [None] * world
         dist.all_gather_object(gathered, own)

@@ -34,7 +34,7 @@ if world > 1:
     t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
 if rank == 0:
     print(json.dumps({"metric": "Jacobi pressure relaxation, slab decomposition", "grid": [n, n], "n_gpus": world, "sweeps": done,
-                      "sweeps_per_pass": slab.nsw_max, "seconds": dt, "us_per_sweep": 1e6 * dt / done,
+                      "sweeps_per_pass": slab.nsw_max, "halo_rows": slab.part.halo, "seconds": dt, "us_per_sweep": 1e6 * dt / done,
                       "value": n * n * done / dt / 1e9, "unit": "GLUP/s", "scaling": "strong",
                       "algorithmic_GBs": 24 * n * n * done / dt / 1e9, "last_rms": rms,
                       "halo_bytes_per_pass_per_neighbour": slab.part.halo * (n + 2) * 8}))
