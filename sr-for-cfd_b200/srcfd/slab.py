@@ -155,7 +155,7 @@ class GpuSlab:
 
     def __init__(self, nx: int, ny: int, dx: float, dy: float, dt: float, rho: float, Var_global: np.ndarray,
                  Ff_global: np.ndarray, world: int, rank: int, device: int = 0, halo: Optional[int] = None,
-                 passes_per_exchange: int = 4):
+                 passes_per_exchange: int = 8):
         from . import _capi as capi
         self.capi = capi
         # the halo depth is the number of sweeps per pass of the kernel for a grid of the LOCAL size

@@ -20,7 +20,8 @@ if world > 1:
 rng = np.random.default_rng(0)
 Var = np.zeros((3, n + 2, n + 2)); Var[2] = rng.uniform(-1, 1, (n + 2, n + 2))
 Ff = 1e-3 * rng.uniform(-1, 1, (4, n + 2, n + 2))
-slab = GpuSlab(n, n, 1.0 / n, 1.0 / n, 1e-3, 1.0, Var, Ff, world, rank, device=local)
+slab = GpuSlab(n, n, 1.0 / n, 1.0 / n, 1e-3, 1.0, Var, Ff, world, rank, device=local,
+               passes_per_exchange=int(os.environ.get("SLAB_M", "8")))
 del Var, Ff
 slab.solve(tol=0.0, max_iter=2 * max(1, slab.nsw_max))          # warm-up (also builds the right-hand side)
 torch.cuda.synchronize()
