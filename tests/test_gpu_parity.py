@@ -184,6 +184,33 @@ def test_jacobi_temporally_blocked_pressure_bit_exact(K, env, monkeypatch):
         kernels._cache.clear()
 
 
+def test_random_shapes_and_caps_bit_exact(K):
+    """Seeded sweep over grid shapes (1..70 rows/columns, the ragged cases of warps, bands and tiles), sweep caps and
+    tolerances: pressure in reference and Jacobi order, upwind and QUICK momentum in reference order, against the oracle."""
+    rng = np.random.default_rng(2024)
+    for trial in range(20):
+        Nx, Ny = int(rng.integers(1, 71)), int(rng.integers(1, 71))
+        cap = int(rng.integers(1, 40))
+        tol = float(10.0 ** rng.uniform(-8, 1))
+        Var, VarOld, Ff = rnd_state(1000 + trial, Nx, Ny, ff_scale=float(10.0 ** rng.uniform(-4, -1)))
+        dx, dy = float(rng.uniform(0.5, 2.0)) / Nx, float(rng.uniform(0.5, 2.0)) / Ny
+        volp, dt, nu, rho = dx * dy, float(10.0 ** rng.uniform(-4, -2)), float(10.0 ** rng.uniform(-3, -1)), 1.0
+        for oname, ocode in (("GS_LEX", O.ORDER_GS_LEX), ("JACOBI", O.ORDER_JACOBI)):
+            A, B = Var.copy(), Var.copy()
+            n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, dt, rho, volp, sweep_order=oname, tolerance=tol, max_iter=cap)
+            m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, dt, rho, volp, order=ocode, tolerance=tol, max_iter=cap)
+            assert n == m and np.array_equal(A, B), ("pressure", oname, trial, Nx, Ny, cap, tol, n, m)
+        k = trial & 1
+        A, B = Var.copy(), Var.copy()
+        n = K.solve_momentum_upwind(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=cap)
+        m = O.solve_momentum_upwind(B, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=cap)
+        assert n == m and np.array_equal(A, B), ("upwind", trial, Nx, Ny, cap, tol, n, m)
+        A, B = Var.copy(), Var.copy()
+        n = K.solve_momentum_quick(A, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=cap)
+        m = O.solve_momentum_quick(B, VarOld, Ff, k, Nx, Ny, dx, dy, dt, nu, volp, tolerance=tol, max_iter=cap)
+        assert n == m and np.array_equal(A, B), ("quick", trial, Nx, Ny, cap, tol, n, m)
+
+
 def test_break_semantics_and_rollback(K):
     """Exact 'stop after the first sweep with rms < tol' behaviour, including the speculative-group
     rollback of the wavefront order (the cached handle carries the previous call's sweep count as its guess)."""
