@@ -181,6 +181,7 @@ class GpuSlab:
         ptrs = self.h.device_ptrs()
         self.p_ptr = ptrs[0] + 2 * (self.part.nx_local + 2) * self.pitch * 8       # plane k = 2
         self._sums = None
+        self._ext = None
 
     # rows as torch tensors aliasing the library's memory
     def _rows(self, first_row: int, nrows: int):
@@ -214,10 +215,10 @@ class GpuSlab:
         """(nslots, 8) per-sweep sums of the last block, summed over the ranks (one collective, one synchronisation)."""
         import torch.distributed as dist
         t = self._sums_tensor()
-        self.h.synchronize()
-        if self.part.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t[:nslots].cpu().numpy()
+        with self._stream():
+            if self.part.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t[:nslots].cpu().numpy()                  # the one synchronisation of a block
 
     def read_sums(self, n: int) -> np.ndarray:
         """Per-sweep sums of the last pass (this slab's owned rows), copied to the host."""
@@ -227,13 +228,20 @@ class GpuSlab:
     def commit(self):
         self.h.k_jacobi_commit()
 
+    def _stream(self):
+        """The library's own stream as a torch stream: collectives issued under it are ordered with the kernels, so the
+        block loop needs no host synchronisation besides reading the reduced sums."""
+        import torch
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self.h.stream(), device=f"cuda:{self.h.params.device}")
+        return torch.cuda.stream(self._ext)
+
     def exchange(self):
         """Owned edge rows -> neighbours' halo rows (NCCL point-to-point, both directions in one batch)."""
         import torch.distributed as dist
         P = self.part
         if P.world == 1:
             return
-        self.h.synchronize()
         ops = []
         if P.lo:        # neighbour above: send my first H owned rows, receive its last H owned rows into my upper halo
             ops += [dist.P2POp(dist.isend, self._rows(P.local_own0, P.halo), P.rank - 1),
@@ -241,18 +249,17 @@ class GpuSlab:
         if P.hi:
             ops += [dist.P2POp(dist.isend, self._rows(P.local_own1 - P.halo + 1, P.halo), P.rank + 1),
                     dist.P2POp(dist.irecv, self._rows(P.local_own1 + 1, P.halo), P.rank + 1)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        import torch
-        torch.cuda.current_stream().synchronize()
+        with self._stream():
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()                                     # stream-level wait: the next pass is ordered after the receive
 
     def allreduce_sum(self, v: np.ndarray) -> np.ndarray:
         import torch, torch.distributed as dist
         t = self._sums_tensor()[0]
-        self.h.synchronize()                                 # the pass ran on the library's stream
-        if self.part.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t[: len(v)].cpu().numpy()
+        with self._stream():
+            if self.part.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t[: len(v)].cpu().numpy()
 
     def solve(self, tol: float = 1e-6, max_iter: int = 1000) -> Tuple[int, float]:
         part = self.part if self.part.world > 1 else SlabPartition(self.part.nx, 1, 0, self.H)

@@ -74,3 +74,53 @@ def test_slab_jacobi_on_gpu_matches_oracle(world):
         assert all(n == m for n, _ in res), (world, tol, cap, res, m)
         assert np.array_equal(rows, B[2, 1:-1]), (world, tol, cap, np.max(np.abs(rows - B[2, 1:-1])))
         for s in slabs: s.h.close()
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import torch, torch.distributed as dist
+    from srcfd.slab import GpuSlab
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    nx, ny = 256, 200
+    rng = np.random.default_rng(4)
+    Var = rng.uniform(-1, 1, (3, nx + 2, ny + 2)); Ff = 0.05 * rng.uniform(-1, 1, (4, nx + 2, ny + 2))
+    out = []
+    for tol, cap in ((0.0, 70), (60.0, 300)):
+        s = GpuSlab(nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0, Var, Ff, world, rank, device=rank, passes_per_exchange=2)
+        n, rms = s.solve(tol, cap)
+        rows = [None] * world
+        dist.all_gather_object(rows, s.owned_rows())
+        out.append((n, np.concatenate(rows, axis=0)))
+        s.h.close()
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_nccl_slab_matches_oracle():
+    """The real thing: two processes, two GPUs, NCCL halo exchange and all-reduce (skipped on a single-GPU box)."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120); assert p.exitcode == 0
+    nx, ny = 256, 200
+    rng = np.random.default_rng(4)
+    Var = rng.uniform(-1, 1, (3, nx + 2, ny + 2)); Ff = 0.05 * rng.uniform(-1, 1, (4, nx + 2, ny + 2))
+    for (tol, cap), (n, rows) in zip(((0.0, 70), (60.0, 300)), got):
+        B = Var.copy()
+        m = O.solve_pressure(B, Ff, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0, 1.0 / (nx * ny), order=O.ORDER_JACOBI, tolerance=tol, max_iter=cap)
+        assert n == m, (tol, cap, n, m)
+        assert np.array_equal(rows, B[2, 1:-1]), (tol, cap, np.max(np.abs(rows - B[2, 1:-1])))
