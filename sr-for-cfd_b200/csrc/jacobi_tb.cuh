@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb(JtbArgs ja) {
 // ---- one pass on its own (slab decomposition, srcfd/slab.py): no grid-wide barrier, so an ordinary launch -------------
 // nsw (<= H) sweeps from the plane to the scratch plane; per-CTA residual sums of every sweep, counted over rows
 // [res_r0, res_r1] only (a slab's halo rows are relaxed too, but belong to the neighbour).
+// The last CTA to finish adds the per-CTA partial sums up, in CTA order (deterministic), into sums[0..nsw).
 template <int H>
-__global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int nsw, int res_r0, int res_r1) {
+__global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int nsw, int res_r0, int res_r1, double* __restrict__ sums,
+                                                                unsigned* __restrict__ ticket) {
     const SolveArgs& a = ja.s;
     if (a.ctrl->stop) return;
     extern __shared__ double smem[];
@@ -244,14 +246,20 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int 
         const double tot = block_sum(acc[t], red);
         if (threadIdx.x == 0) ja.partials[(size_t)t * gridDim.x + blockIdx.x] = tot;
     }
-}
-// sums[t] = sum over CTAs in index order
-__global__ void k_jacobi_tb_sums(JtbArgs ja, int nparts, int nsw, double* __restrict__ sums) {
-    if (ja.s.ctrl->stop) return;
-    if ((int)threadIdx.x < nsw) {
-        double s = 0.0;
-        for (int b = 0; b < nparts; ++b) s += ja.partials[(size_t)threadIdx.x * nparts + b];
-        sums[threadIdx.x] = s;
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();                                     // partials visible before the ticket
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if ((int)threadIdx.x < nsw) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ja.partials + (size_t)threadIdx.x * gridDim.x + b);
+            sums[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;                  // ready for the next pass (stream order)
     }
 }
 // boundary cells of the plane -> scratch plane (a pass writes interior cells only)

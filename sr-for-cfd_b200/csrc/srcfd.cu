@@ -86,7 +86,9 @@ struct srcfd_handle {
     size_t jtb_smem = 0;
     const void* jtb_fn = nullptr;
     double* jtb_partials = nullptr;
-    double* jtb_sums = nullptr;         // [8] per-sweep residual sums of the last single pass (device)
+    double* jtb_sums = nullptr;         // [16 slots][8] per-sweep residual sums of single passes (device)
+    unsigned* jtb_ticket = nullptr;     // last-CTA-done counter of the single-pass kernel
+    bool jtb_ghosts_valid = false;      // boundary cells of the scratch plane match the pressure plane
     const void* jtb_pass_fn = nullptr;
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
@@ -314,7 +316,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
-    cudaFree(h->jtb_partials); cudaFree(h->jtb_sums);
+    cudaFree(h->jtb_partials); cudaFree(h->jtb_sums); cudaFree(h->jtb_ticket);
     cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
     cudaFree(h->sweeps1); cudaFree(h->sweeps2);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
@@ -375,7 +377,8 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
-    if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream)); }
+    if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream));
+                      CKB(cudaMalloc(&h->jtb_ticket, sizeof(unsigned))); CKB(cudaMemsetAsync(h->jtb_ticket, 0, sizeof(unsigned), h->stream)); }
     if (h->gs3) {
         const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
         CKB(cudaMalloc(&h->gs3_ll, llb));
@@ -434,7 +437,7 @@ int srcfd_stream(srcfd_handle* h, uint64_t* stream) {
 int srcfd_upload(srcfd_handle* h, const double* Var, const double* VarOld, const double* Ff, const double* residual) {
     CKH(h);
     const size_t P = (size_t)h->K.plane;
-    if (Var) { CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream)); h->ghosts_fresh = false; }
+    if (Var) { CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream)); h->ghosts_fresh = false; h->jtb_ghosts_valid = false; }
     if (VarOld) CK(cudaMemcpyAsync(h->VarOld, VarOld, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
     if (Ff) CK(cudaMemcpyAsync(h->Ff, Ff, sizeof(double) * 4 * P, cudaMemcpyHostToDevice, h->stream));
     if (residual) CK(cudaMemcpyAsync((char*)h->ctrl + offsetof(Ctrl, residual), residual, sizeof(double) * 3, cudaMemcpyHostToDevice, h->stream));
@@ -491,6 +494,7 @@ static int l_copy_new_to_old(srcfd_handle* h) {
     return SRCFD_OK;
 }
 static int l_apply_bc(srcfd_handle* h, int k, int mode = 0) {
+    h->jtb_ghosts_valid = false;
     const int n = std::max(h->K.nx, h->K.ny);
     k_apply_bc<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Var, k, h->K, h->bc, mode, h->ctrl);
     LAUNCH_CHECK(h);
@@ -556,6 +560,7 @@ static int ev_drain(srcfd_handle* h) {
 
 // One inner solve: op in {OP_PRESSURE, OP_UPWIND, OP_QUICK} on plane k, counters in slot.
 static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = false) {
+    h->jtb_ghosts_valid = false;                            // the solves below use the scratch plane
     SolveArgs a;
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
@@ -838,13 +843,16 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
     ja.partials = h->jtb_partials;
     // boundary cells of the scratch plane must match the plane (the pass only writes interior cells)
-    k_jacobi_tb_ghosts<<<(std::max(h->K.nx, h->K.ny) + 2 + 127) / 128, 128, 0, h->stream>>>(a);
-    LAUNCH_CHECK(h);
-    void* args[] = {&ja, &nsweeps, &own_row0, &own_row1};
+    if (!h->jtb_ghosts_valid) {                             // they only change with the plane's own boundary cells
+        k_jacobi_tb_ghosts<<<(std::max(h->K.nx, h->K.ny) + 2 + 127) / 128, 128, 0, h->stream>>>(a);
+        LAUNCH_CHECK(h);
+        h->launches += 1;
+        h->jtb_ghosts_valid = true;
+    }
+    double* sums_dev = h->jtb_sums + 8 * slot;
+    void* args[] = {&ja, &nsweeps, &own_row0, &own_row1, &sums_dev, &h->jtb_ticket};
     CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
-    k_jacobi_tb_sums<<<1, 32, 0, h->stream>>>(ja, h->jtb_grid, nsweeps, h->jtb_sums + 8 * slot);
-    LAUNCH_CHECK(h);
-    h->launches += 2;
+    h->launches += 1;
     if (commit) {
         k_jacobi_tb_commit<<<std::max(1, h->tail_blocks / 4), 256, 0, h->stream>>>(a);
         LAUNCH_CHECK(h);
