@@ -76,6 +76,7 @@ struct srcfd_handle {
     // third-generation pressure solve (inner_gs3.cuh): full-height groups, diagonal streams
     bool gs3 = false;            // usable for this grid (SRCFD_GS3=0 disables)
     int gs3_K = 3, gs3_RP = 0, gs3_ND = 0, gs3_nbuf = 4, gs3_grid = 0;
+    int gs3_stride = 512, gs3_kmax = 4;   // row slots per diagonal and largest group of the kernel instance in use
     size_t gs3_smem = 0;
     const void* gs3_fn = nullptr;
     uint4* gs3_ll = nullptr;
@@ -225,16 +226,23 @@ static int plan_gs3(srcfd_handle* h) {
     if (const char* e = getenv("SRCFD_GS3")) if (atoi(e) == 0) return SRCFD_OK;
     const int nx = h->p.nx, ny = h->p.ny;
     const int RP = ((nx + 31) / 32) * 32 + 32;          // threads: one per row, plus the ghost warp
-    if (RP > WF3_MAXT || h->inner_cap + 2 >= 4096) return SRCFD_OK;
-    if (const char* e = getenv("SRCFD_K3")) h->gs3_K = std::max(1, std::min(WF3_KMAX, atoi(e)));
+    if (h->inner_cap + 2 >= 4096) return SRCFD_OK;
+    // two instances: up to 480 rows with groups of up to 4 sweeps (128 registers per thread), up to 990 rows with
+    // one sweep per group (1024 threads leave 64 registers per thread)
+    if (RP <= 512) { h->gs3_stride = 512; h->gs3_kmax = 4; }
+    else if (RP <= 1024 && nx + 2 <= 1024 - 4) { h->gs3_stride = 1024; h->gs3_kmax = 1; h->gs3_nbuf = 2; }
+    else return SRCFD_OK;
+    h->gs3_K = std::min(h->gs3_K, h->gs3_kmax);
+    if (const char* e = getenv("SRCFD_K3")) h->gs3_K = std::max(1, std::min(h->gs3_kmax, atoi(e)));
     if (const char* e = getenv("SRCFD_NBUF")) h->gs3_nbuf = std::max(2, atoi(e));
     h->gs3_RP = RP; h->gs3_ND = nx + ny + 2;
-    const size_t per = sizeof(uint4) * (size_t)h->gs3_ND * WF3_RP;
+    const size_t per = sizeof(uint4) * (size_t)h->gs3_ND * h->gs3_stride;
     while (h->gs3_nbuf > 2 && per * h->gs3_nbuf > ((size_t)1 << 31)) --h->gs3_nbuf;
     if (per * h->gs3_nbuf > ((size_t)1 << 31)) return SRCFD_OK;
-    h->gs3_smem = sizeof(double) * ((size_t)(3 * (WF3_KMAX + 1) + WF3_RQ) * WF3_RP + 2 * (size_t)(ny + 2) + WF3_KMAX * 32);
+    h->gs3_smem = sizeof(double) * ((size_t)(3 * (h->gs3_kmax + 1) + WF3_RQ) * h->gs3_stride + 2 * (size_t)(ny + 2) + h->gs3_kmax * 32);
     if (h->gs3_smem > 200 * 1024) return SRCFD_OK;
-    h->gs3_fn = RP <= 448 ? (const void*)k_solve_gs3<448> : (const void*)k_solve_gs3<512>;   // 448 threads: 144 registers each
+    h->gs3_fn = RP <= 448 ? (const void*)k_solve_gs3<448, 512, 4> : RP <= 512 ? (const void*)k_solve_gs3<512, 512, 4>
+                                                                              : (const void*)k_solve_gs3<1024, 1024, 1>;
     if (int rc = raise_smem_limit(h->dev, h->gs3_fn, h->gs3_smem)) return rc;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->gs3_fn, RP, h->gs3_smem));
@@ -380,10 +388,10 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream));
                       CKB(cudaMalloc(&h->jtb_ticket, sizeof(unsigned))); CKB(cudaMemsetAsync(h->jtb_ticket, 0, sizeof(unsigned), h->stream)); }
     if (h->gs3) {
-        const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * WF3_RP;
+        const size_t llb = sizeof(uint4) * ((size_t)h->gs3_nbuf * h->gs3_ND + WF3_PAD_HI) * h->gs3_stride;
         CKB(cudaMalloc(&h->gs3_ll, llb));
         CKB(cudaMemsetAsync(h->gs3_ll, 0, llb, h->stream));
-        const size_t rb = sizeof(double) * (size_t)(WF3_PAD_LO + h->gs3_ND + WF3_PAD_HI) * WF3_RP;
+        const size_t rb = sizeof(double) * (size_t)(WF3_PAD_LO + h->gs3_ND + WF3_PAD_HI) * h->gs3_stride;
         CKB(cudaMalloc(&h->gs3_rhsS, rb));
         CKB(cudaMemsetAsync(h->gs3_rhsS, 0, rb, h->stream));
         CKB(cudaMalloc(&h->gs3_epoch, sizeof(unsigned long long)));
@@ -573,7 +581,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         Gs3Args g3;
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
         g3.s.prog = h->trace ? h->prog : nullptr;      // this kernel has no progress flags: non-null only asks it to count polls
-        g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * WF3_RP; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
+        g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * h->gs3_stride; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
         g3.skip_idle = getenv("SRCFD_SKIP_IDLE") ? atoi(getenv("SRCFD_SKIP_IDLE")) : 1;
         g3.pretouch = getenv("SRCFD_PRETOUCH") ? atoi(getenv("SRCFD_PRETOUCH")) : 1;
         void* args3[] = {&g3};
