@@ -133,6 +133,32 @@ int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, 
 /* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
 int srcfd_k_implicit_solve(srcfd_handle *h);
 
+/* ---- batched small-grid solves: the coarse stage of the ML-accelerated workflow ---------------------------------
+ * run_coarse_simulation (PyCFD_ML_accelerated.py:696-761 / bfs_ml_accelerated.py:893-977) builds a CFDSolver on the
+ * lr_dim x lr_dim mesh (10x10), which zero-initialises (_initialize_fields) and runs solve() for up to 100 000 outer
+ * iterations.  srcfd_coarse_solve_batch does that for n_cases independent cases in ONE launch: one CTA per case, the
+ * whole state in shared memory, the reference sweep order (results bit-identical to CFDSolver.solve with
+ * NUMBA_NUM_THREADS=1).  All cases share nx, ny and device; everything else (Re, dt, scheme, BCs, BFS inlet, relaxation)
+ * is per case.  crit = n_cases x {u, v, p}.  Var / VarOld / Ff: (n_cases, 3|3|4, nx+2, ny+2) host arrays that receive
+ * the final state (VarOld, Ff may be NULL); resume != 0 starts from their contents instead of zero fields.
+ * hist (may be NULL): n_cases x hist_cap x 3 rms triplets sampled when count % 100 == 0.  *ms = device time of the
+ * launch.  The grid must fit shared memory (srcfd_coarse_smem_bytes <= the device's opt-in limit; about 30x30). */
+typedef struct srcfd_coarse_result {
+    int64_t iterations;
+    int32_t converged, nan_flag;     /* nan_flag: the reference raises ValueError at this iteration */
+    double  rms[3];                  /* last sqrt(residual/(nx*ny))/dt triplet */
+    int64_t total_sweeps[3];         /* inner sweeps executed (u, v, p) */
+    int64_t n_hist;
+    double  last_inner_rms[3];
+    double  residual[3];             /* CFDSolver.residual after the last iteration */
+    int32_t last_sweeps[3];
+    int32_t reserved_;
+} srcfd_coarse_result;
+int srcfd_coarse_smem_bytes(int nx, int ny, uint64_t *bytes);
+int srcfd_coarse_solve_batch(const srcfd_params *params, int n_cases, int64_t max_iterations, const double *crit,
+                             int resume, double *Var, double *VarOld, double *Ff, srcfd_coarse_result *results,
+                             double *hist, int64_t hist_cap, double *ms);
+
 /* ---- introspection for benchmarks ---------------------------------------------------------- */
 /* CUDA-event stopwatch on the handle's stream: start records an event, stop records a second one,
  * waits for it and returns the device time between them in milliseconds. */

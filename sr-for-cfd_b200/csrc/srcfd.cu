@@ -18,6 +18,7 @@
 #include "inner_gs2.cuh"
 #include "inner_gs3.cuh"
 #include "jacobi_tb.cuh"
+#include "coarse_batch.cuh"
 
 using namespace srcfd;
 
@@ -960,3 +961,104 @@ int srcfd_timing_read(srcfd_handle* h, double* pressure_ms, int64_t* pressure_la
 }
 
 }  // extern "C"
+
+// ---- batched small-grid solves (coarse_batch.cuh) ---------------------------------------------------------------
+extern "C" int srcfd_coarse_smem_bytes(int nx, int ny, uint64_t* bytes) {
+    if (nx < 1 || ny < 1 || !bytes) return fail(SRCFD_ERR_ARG, "bad argument");
+    const long long P = (long long)(nx + 2) * (ny + 2);
+    const int M2 = (ny + 1) / 2, M3 = (ny + 2) / 3;
+    const int ring2 = (nx - 1 + 2 * M2 - 1) / 2 + 2, ring3 = (nx - 1 + 3 * M3 - 1) / 3 + 2;
+    const long long ring = std::max(ring2, ring3), stride = (long long)nx * M2;
+    *bytes = (uint64_t)(12 * P + ring * stride) * sizeof(double);
+    return SRCFD_OK;
+}
+
+extern "C" int srcfd_coarse_solve_batch(const srcfd_params* params, int n_cases, int64_t max_iterations, const double* crit,
+                                        int resume, double* Var, double* VarOld, double* Ff, srcfd_coarse_result* results,
+                                        double* hist, int64_t hist_cap, double* ms) {
+    if (!params || n_cases < 1 || !crit || !Var || !results) return fail(SRCFD_ERR_ARG, "null argument");
+    if (resume && (!VarOld || !Ff)) return fail(SRCFD_ERR_ARG, "resume needs Var, VarOld and Ff");
+    if (max_iterations < 0 || hist_cap < 0) return fail(SRCFD_ERR_ARG, "negative count");
+    const int nx = params[0].nx, ny = params[0].ny, dev = params[0].device;
+    std::vector<CoarseCase> cases((size_t)n_cases);
+    for (int c = 0; c < n_cases; ++c) {
+        const srcfd_params& p = params[c];
+        if (int rc = check_params(&p)) return rc;
+        if (p.nx != nx || p.ny != ny || p.device != dev) return fail(SRCFD_ERR_ARG, "all cases of a batch share nx, ny and device");
+        if (p.sweep_order != SRCFD_ORDER_GS_LEX) return fail(SRCFD_ERR_ARG, "the batched solver runs the reference sweep order only");
+        CoarseCase& cs = cases[(size_t)c];
+        cs.K = make_consts(p); cs.bc = make_bc(p);
+        cs.scheme = p.scheme; cs.relax_enabled = p.relax_enabled;
+        for (int k = 0; k < 3; ++k) { cs.relax[k] = p.relax[k]; cs.crit[k] = crit[3 * c + k]; }
+        cs.inner_tol = p.inner_tol; cs.inner_max = p.inner_max; cs.max_iterations = max_iterations;
+    }
+    uint64_t smem = 0;
+    if (int rc = srcfd_coarse_smem_bytes(nx, ny, &smem)) return rc;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (smem + 2048 > (uint64_t)prop.sharedMemPerBlockOptin)
+        return fail(SRCFD_ERR_ARG, "grid too large for the shared-memory resident batched solver (use srcfd_create/srcfd_solve)");
+    const int M2 = (ny + 1) / 2, M3 = (ny + 2) / 3;
+    const int ring = std::max((nx - 1 + 2 * M2 - 1) / 2 + 2, (nx - 1 + 3 * M3 - 1) / 3 + 2), stride = nx * M2;
+    const int threads = ((stride + 31) / 32) * 32 + 32;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, (const void*)k_coarse_solve));
+    if (threads > fa.maxThreadsPerBlock) return fail(SRCFD_ERR_ARG, "grid too large for one CTA per case");
+    if (int rc = raise_smem_limit(dev, (const void*)k_coarse_solve, (size_t)smem)) return rc;
+
+    const size_t P = (size_t)(nx + 2) * (ny + 2), nV = 3 * P * (size_t)n_cases, nF = 4 * P * (size_t)n_cases;
+    CoarseCase* d_cases = nullptr; CoarseOut* d_out = nullptr;
+    double *d_Var = nullptr, *d_VarOld = nullptr, *d_Ff = nullptr, *d_hist = nullptr;
+    cudaStream_t st = nullptr; cudaEvent_t ea = nullptr, eb = nullptr;
+    int rc = SRCFD_OK;
+    auto body = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
+        CK(cudaMalloc(&d_cases, sizeof(CoarseCase) * (size_t)n_cases));
+        CK(cudaMalloc(&d_out, sizeof(CoarseOut) * (size_t)n_cases));
+        CK(cudaMalloc(&d_Var, sizeof(double) * nV)); CK(cudaMalloc(&d_VarOld, sizeof(double) * nV));
+        CK(cudaMalloc(&d_Ff, sizeof(double) * nF));
+        if (hist && hist_cap > 0) CK(cudaMalloc(&d_hist, sizeof(double) * 3 * (size_t)hist_cap * (size_t)n_cases));
+        CK(cudaMemcpyAsync(d_cases, cases.data(), sizeof(CoarseCase) * (size_t)n_cases, cudaMemcpyHostToDevice, st));
+        if (resume) {
+            CK(cudaMemcpyAsync(d_Var, Var, sizeof(double) * nV, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_VarOld, VarOld, sizeof(double) * nV, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_Ff, Ff, sizeof(double) * nF, cudaMemcpyHostToDevice, st));
+        }
+        CK(cudaEventRecord(ea, st));
+        k_coarse_solve<<<n_cases, threads, (size_t)smem, st>>>(d_cases, d_Var, d_VarOld, d_Ff, d_out, d_hist,
+                                                               (long long)hist_cap, ring, stride, resume ? 1 : 0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(eb, st));
+        std::vector<CoarseOut> outs((size_t)n_cases);
+        CK(cudaMemcpyAsync(outs.data(), d_out, sizeof(CoarseOut) * (size_t)n_cases, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(Var, d_Var, sizeof(double) * nV, cudaMemcpyDeviceToHost, st));
+        if (VarOld) CK(cudaMemcpyAsync(VarOld, d_VarOld, sizeof(double) * nV, cudaMemcpyDeviceToHost, st));
+        if (Ff) CK(cudaMemcpyAsync(Ff, d_Ff, sizeof(double) * nF, cudaMemcpyDeviceToHost, st));
+        if (d_hist) CK(cudaMemcpyAsync(hist, d_hist, sizeof(double) * 3 * (size_t)hist_cap * (size_t)n_cases, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (ms) { float f = 0.f; CK(cudaEventElapsedTime(&f, ea, eb)); *ms = f; }
+        for (int c = 0; c < n_cases; ++c) {
+            const CoarseOut& o = outs[(size_t)c];
+            srcfd_coarse_result& r = results[c];
+            r.iterations = o.iterations; r.converged = o.converged; r.nan_flag = o.nan_flag; r.n_hist = o.n_hist;
+            for (int k = 0; k < 3; ++k) {
+                r.rms[k] = o.rms[k]; r.total_sweeps[k] = o.total_sweeps[k]; r.last_inner_rms[k] = o.last_inner_rms[k];
+                r.residual[k] = o.residual[k]; r.last_sweeps[k] = o.last_sweeps[k];
+            }
+        }
+        return SRCFD_OK;
+    };
+    rc = body();
+    if (d_cases) cudaFree(d_cases);
+    if (d_out) cudaFree(d_out);
+    if (d_Var) cudaFree(d_Var);
+    if (d_VarOld) cudaFree(d_VarOld);
+    if (d_Ff) cudaFree(d_Ff);
+    if (d_hist) cudaFree(d_hist);
+    if (ea) cudaEventDestroy(ea);
+    if (eb) cudaEventDestroy(eb);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}

@@ -44,6 +44,16 @@ class Params(C.Structure):
     ]
 
 
+class CoarseResult(C.Structure):
+    """srcfd_coarse_result (include/srcfd.h)."""
+    _fields_ = [
+        ("iterations", C.c_int64), ("converged", C.c_int32), ("nan_flag", C.c_int32),
+        ("rms", C.c_double * 3), ("total_sweeps", C.c_int64 * 3), ("n_hist", C.c_int64),
+        ("last_inner_rms", C.c_double * 3), ("residual", C.c_double * 3), ("last_sweeps", C.c_int32 * 3),
+        ("reserved_", C.c_int32),
+    ]
+
+
 _dp = C.POINTER(C.c_double)
 _lib = None
 
@@ -57,6 +67,7 @@ SYMBOLS = [
     "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
     "srcfd_k_solve_pressure", "srcfd_jacobi_pass_max", "srcfd_k_jacobi_pass", "srcfd_k_jacobi_commit", "srcfd_jacobi_sums_ptr", "srcfd_k_jacobi_snapshot", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
+    "srcfd_coarse_smem_bytes", "srcfd_coarse_solve_batch",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
     "srcfd_sr_last_error", "srcfd_sr_create", "srcfd_sr_destroy", "srcfd_sr_set_encoder", "srcfd_sr_set_decoder",
     "srcfd_sr_encode", "srcfd_sr_decode", "srcfd_sr_predict", "srcfd_sr_decode_device", "srcfd_sr_launch_count",
@@ -302,3 +313,45 @@ class Handle:
         pm, mm, pn, mn = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
         check(lib().srcfd_timing_read(self._h, C.byref(pm), C.byref(pn), C.byref(mm), C.byref(mn)))
         return dict(pressure_ms=pm.value, pressure_launches=pn.value, momentum_ms=mm.value, momentum_launches=mn.value)
+
+
+def coarse_smem_bytes(nx: int, ny: int) -> int:
+    n = C.c_uint64(0)
+    check(lib().srcfd_coarse_smem_bytes(int(nx), int(ny), C.byref(n)))
+    return n.value
+
+
+def coarse_solve_batch(params, max_iterations: int, crit, hist_cap: int = 0, state=None):
+    """srcfd_coarse_solve_batch: CFDSolver(...).solve() of len(params) small cases in one launch (one CTA per case).
+
+    params: sequence of Params sharing nx, ny, device; crit: (n, 3) or (3,) outer criteria {u, v, p}.
+    state: optional (Var, VarOld, Ff) arrays (n, 3|3|4, nx+2, ny+2) to resume from (updated in place).
+    Returns dict(Var, VarOld, Ff, iterations, converged, nan, rms, total_sweeps, hist, ms)."""
+    n = len(params)
+    if n < 1:
+        raise ValueError("no cases")
+    arr = (Params * n)(*params)
+    nx, ny = params[0].nx, params[0].ny
+    crit = np.ascontiguousarray(np.broadcast_to(np.asarray(crit, dtype=np.float64), (n, 3)))
+    if state is None:
+        Var = np.zeros((n, 3, nx + 2, ny + 2)); VarOld = np.zeros_like(Var); Ff = np.zeros((n, 4, nx + 2, ny + 2))
+    else:
+        Var, VarOld, Ff = state
+        assert Var.shape == (n, 3, nx + 2, ny + 2) and VarOld.shape == Var.shape and Ff.shape == (n, 4, nx + 2, ny + 2)
+    res = (CoarseResult * n)()
+    hist = np.zeros((n, max(hist_cap, 1), 3)) if hist_cap > 0 else None
+    ms = C.c_double(0.0)
+    check(lib().srcfd_coarse_solve_batch(arr, n, C.c_int64(int(max_iterations)), _ptr(crit), int(state is not None),
+                                         _ptr(Var), _ptr(VarOld), _ptr(Ff), res, _ptr(hist), C.c_int64(int(hist_cap)),
+                                         C.byref(ms)))
+    return dict(Var=Var, VarOld=VarOld, Ff=Ff,
+                iterations=np.array([r.iterations for r in res], dtype=np.int64),
+                converged=np.array([bool(r.converged) for r in res]),
+                nan=np.array([bool(r.nan_flag) for r in res]),
+                rms=np.array([[r.rms[k] for k in range(3)] for r in res]),
+                last_inner_rms=np.array([[r.last_inner_rms[k] for k in range(3)] for r in res]),
+                total_sweeps=np.array([[r.total_sweeps[k] for k in range(3)] for r in res], dtype=np.int64),
+                residual=np.array([[r.residual[k] for k in range(3)] for r in res]),
+                last_sweeps=np.array([[r.last_sweeps[k] for k in range(3)] for r in res], dtype=np.int64),
+                hist=[hist[i, :res[i].n_hist].copy() for i in range(n)] if hist is not None else None,
+                ms=ms.value)

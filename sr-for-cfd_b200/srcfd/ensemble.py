@@ -57,22 +57,59 @@ def shard_cases(cases: Sequence, rank: int, world: int) -> List:
     return [c for i, c in enumerate(cases) if i % world == rank]
 
 
-def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optional[dict] = None, keep_fields=True) -> CaseResult:
-    """Coarse solve -> SR warm start -> fine solve for one case on one GPU (the reference's per-case workflow)."""
+def _case_bc(spec: CaseSpec):
+    from . import ldc
+    if spec.kind != "ldc2":
+        return None
+    bc = ldc.BoundaryConditions()
+    bc.u_boundaries['bottom'] = ldc.BoundaryCondition('dirichlet', 1.0)     # PyCFD_ML_accelerated.py:1387-1392
+    return bc
+
+
+def coarse_stage(cases: Sequence[CaseSpec], device: int = 0, lr_dim: int = 10, max_iterations: int = 2000) -> List[dict]:
+    """run_coarse_simulation (LDC.py:696-761 / BFS.py:893-977) of every case in ONE launch: one CTA per case
+    (srcfd_coarse_solve_batch), each bit-identical to its own CFDSolver(lr_dim x lr_dim).solve().
+    Returns the reference's coarse field dicts {'u','v','p'} of shape (lr_dim, lr_dim), in case order."""
+    from . import _capi as capi, bfs, ldc, solver as S
+    if not cases:
+        return []
+    params, crit = [], []
+    for spec in cases:
+        wf = (bfs if spec.kind == "bfs" else ldc)._wf
+        dt, scheme, lx, ly = wf._defaults(None, None, None, None)
+        s_mesh = S.MeshParameters(nx=lr_dim, ny=lr_dim, lx=lx, ly=ly)
+        cc = {'u': 1e-6, 'v': 1e-6, 'p': 1e-6, 'continuity': 1e-6}
+        if wf.bfs:
+            st = S.BFSSolverSettings(dt=dt, scheme=scheme, max_iterations=max_iterations, convergence_criteria=cc)
+            params.append(S.make_params(s_mesh, S.FluidProperties(Re=spec.Re, rho=1.0), st, wf._default_bc(), 'BFS',
+                                        1.0, 2.0, 1.0, True, device))
+        else:
+            st = S.SolverSettings(dt=dt, scheme=scheme, max_iterations=max_iterations, convergence_criteria=cc)
+            params.append(S.make_params(s_mesh, S.FluidProperties(Re=spec.Re, rho=1.0), st,
+                                        _case_bc(spec) or wf._default_bc(), None, device=device))
+        crit.append((cc['u'], cc['v'], cc['p']))
+    r = capi.coarse_solve_batch(params, max_iterations, np.array(crit))
+    if r['nan'].any():
+        raise ValueError("Solver failed: NaN/Inf in residuals")
+    return [{n: r['Var'][i, k, 1:-1, 1:-1].T.copy() for k, n in enumerate('uvp')} for i in range(len(cases))]
+
+
+def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optional[dict] = None, keep_fields=True,
+             coarse: Optional[dict] = None) -> CaseResult:
+    """Coarse solve -> SR warm start -> fine solve for one case on one GPU (the reference's per-case workflow).
+    `coarse`: this case's coarse fields when coarse_stage already produced them."""
     from . import bfs, ldc
     mod = bfs if spec.kind == "bfs" else ldc
     wf = mod._wf
     t0 = time.time()
-    bc = None
-    if spec.kind == "ldc2":
-        bc = ldc.BoundaryConditions()
-        bc.u_boundaries['bottom'] = ldc.BoundaryCondition('dirichlet', 1.0)     # PyCFD_ML_accelerated.py:1387-1392
+    bc = _case_bc(spec)
     solver = wf._make_solver(spec.Re, spec.nx, spec.ny, *wf._defaults(None, None, None, None)[:2], None,
                              spec.max_iterations, bc, 1.0, 2.0, 1.0, *wf._defaults(None, None, None, None)[2:], None,
                              device=device, max_ctas=max_ctas)
     if spec.warm_start and sr_files is not None:
-        coarse = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=sr_files.get("coarse_iterations", 2000),
-                                          bc=bc, save=False)
+        if coarse is None:
+            coarse = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=sr_files.get("coarse_iterations", 2000),
+                                              bc=bc, save=False)
         kw = dict(use_aspect_ratio_correction=True, lx=10.0, ly=3.0) if spec.kind == "bfs" else {}
         hr = wf.ml_super_resolution(coarse, 10, spec.nx, sr_files["stats"], sr_files["encoder"], sr_files["decoder"], **kw)
         solver._sync_params()
@@ -91,6 +128,12 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, 
     results: List[Optional[CaseResult]] = [None] * len(cases)
     lock, nxt = threading.Lock(), [0]
     max_ctas = max(1, num_sms // max(1, concurrency)) if concurrency > 1 else 0
+    sr_files = kw.get("sr_files")
+    coarse = [None] * len(cases)
+    if runner is run_case and sr_files is not None and any(c.warm_start for c in cases):
+        warm = [i for i, c in enumerate(cases) if c.warm_start]
+        for i, f in zip(warm, coarse_stage([cases[i] for i in warm], device, 10, sr_files.get("coarse_iterations", 2000))):
+            coarse[i] = f
 
     def worker():
         while True:
@@ -99,7 +142,8 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, 
                 nxt[0] += 1
             if i >= len(cases):
                 return
-            results[i] = runner(cases[i], device=device, max_ctas=max_ctas, **kw)
+            extra = dict(coarse=coarse[i]) if coarse[i] is not None else {}
+            results[i] = runner(cases[i], device=device, max_ctas=max_ctas, **extra, **kw)
 
     threads = [threading.Thread(target=worker) for _ in range(max(1, min(concurrency, len(cases))))]
     for t in threads:

@@ -107,6 +107,52 @@ class BFSSolverSettings(SolverSettings):
 _SIDES = ('left', 'right', 'top', 'bottom')
 
 
+def get_bc_arrays(bc, k: int):
+    """CFDSolver._get_bc_arrays (LDC.py:351-375) for a BoundaryConditions container."""
+    bc_dict = (bc.u_boundaries, bc.v_boundaries, bc.p_boundaries)[min(k, 2)]
+    bc_types = np.array([0 if bc_dict[s].type == 'dirichlet' else 1 for s in _SIDES], dtype=np.int32)
+    bc_values = np.array([bc_dict[s].value for s in _SIDES], dtype=np.float64)
+    return bc_types, bc_values
+
+
+def make_params(mesh, fluid, settings, bc, case_type=None, step_height=1.0, h=2.0, Ub=1.0, relaxed=False,
+                device: int = 0, max_ctas: int = 0) -> capi.Params:
+    """The srcfd_params of one case (what CFDSolver.__init__ of LDC.py:333-349 / BFS.py:473-496 fixes)."""
+    p = capi.Params()
+    m, f, s = mesh, fluid, settings
+    p.nx, p.ny = m.nx, m.ny
+    p.dx, p.dy, p.volp = m.dx, m.dy, m.volp
+    p.dt, p.nu, p.rho = s.dt, f.nu, f.rho
+    p.scheme = capi.SCHEME_QUICK if s.scheme == 'QUICK' else capi.SCHEME_UPWIND
+    for k in range(3):
+        t, v = get_bc_arrays(bc, k)
+        for i in range(4):
+            p.bc_types[k][i] = int(t[i])
+            p.bc_values[k][i] = float(v[i])
+    p.bfs_enabled = int(case_type == 'BFS')
+    p.bfs_step_h, p.bfs_h, p.bfs_Ub = float(step_height), float(h), float(Ub)
+    rf = getattr(s, 'relaxation_factors', None)
+    p.relax_enabled = int(bool(relaxed))
+    rf = rf or {}
+    p.relax[0], p.relax[1], p.relax[2] = rf.get('u', 0.5), rf.get('v', 0.5), rf.get('p', 0.2)
+    p.inner_tol = getattr(s, 'inner_tolerance', 1e-6)
+    p.inner_max = getattr(s, 'inner_max_iter', 1000)
+    order = getattr(s, 'sweep_order', 'GS_LEX')
+    p.sweep_order = capi.ORDERS[order.upper()] if isinstance(order, str) else int(order)
+    p.device, p.max_ctas = device, max_ctas
+    return p
+
+
+_ONE_CTA_SMEM = 227 * 1024 - 2048      # opt-in shared memory per CTA on sm_100a, less the kernel's static part
+_ONE_CTA_THREADS = 640                # register-limited block size of k_coarse_solve
+
+
+def fits_one_cta(nx: int, ny: int) -> bool:
+    """True when srcfd_coarse_solve_batch accepts the grid (state in shared memory, one thread per 2 cells of a row)."""
+    threads = ((nx * ((ny + 1) // 2) + 31) // 32) * 32 + 32
+    return threads <= _ONE_CTA_THREADS and capi.coarse_smem_bytes(nx, ny) <= _ONE_CTA_SMEM
+
+
 # --------------------------------------------------------------------------------------------------
 # CFDSolver
 # --------------------------------------------------------------------------------------------------
@@ -146,35 +192,11 @@ class CFDSolver:
     # ---- parameter marshalling ---------------------------------------------------------------
     def _get_bc_arrays(self, k: int):
         """LDC.py:351-375."""
-        bc_dict = (self.bc.u_boundaries, self.bc.v_boundaries, self.bc.p_boundaries)[min(k, 2)]
-        bc_types = np.array([0 if bc_dict[s].type == 'dirichlet' else 1 for s in _SIDES], dtype=np.int32)
-        bc_values = np.array([bc_dict[s].value for s in _SIDES], dtype=np.float64)
-        return bc_types, bc_values
+        return get_bc_arrays(self.bc, k)
 
     def _params(self) -> capi.Params:
-        p = capi.Params()
-        m, f, s = self.mesh, self.fluid, self.settings
-        p.nx, p.ny = m.nx, m.ny
-        p.dx, p.dy, p.volp = m.dx, m.dy, m.volp
-        p.dt, p.nu, p.rho = s.dt, f.nu, f.rho
-        p.scheme = capi.SCHEME_QUICK if s.scheme == 'QUICK' else capi.SCHEME_UPWIND
-        for k in range(3):
-            t, v = self._get_bc_arrays(k)
-            for i in range(4):
-                p.bc_types[k][i] = int(t[i])
-                p.bc_values[k][i] = float(v[i])
-        p.bfs_enabled = int(getattr(self, 'case_type', None) == 'BFS')
-        p.bfs_step_h, p.bfs_h, p.bfs_Ub = float(self.step_height), float(self.h), float(self.Ub)
-        rf = getattr(s, 'relaxation_factors', None)
-        p.relax_enabled = int(bool(self.relaxed))
-        rf = rf or {}
-        p.relax[0], p.relax[1], p.relax[2] = rf.get('u', 0.5), rf.get('v', 0.5), rf.get('p', 0.2)
-        p.inner_tol = getattr(s, 'inner_tolerance', 1e-6)
-        p.inner_max = getattr(s, 'inner_max_iter', 1000)
-        order = getattr(s, 'sweep_order', 'GS_LEX')
-        p.sweep_order = capi.ORDERS[order.upper()] if isinstance(order, str) else int(order)
-        p.device, p.max_ctas = self.device, self.max_ctas
-        return p
+        return make_params(self.mesh, self.fluid, self.settings, self.bc, getattr(self, 'case_type', None),
+                           self.step_height, self.h, self.Ub, self.relaxed, self.device, self.max_ctas)
 
     def _sync_params(self):
         self._handle.set_params(self._params())
@@ -246,11 +268,14 @@ class CFDSolver:
             print(f"Time step: {self.settings.dt}, Scheme: {self.settings.scheme}")
             print("\nIteration\tU-RMS\t\tV-RMS\t\tP-RMS")
             print("-" * 60)
+        crit, max_it = self._crit(), int(self.settings.max_iterations)
+        if self._fits_one_cta():
+            count = self._solve_resident(crit, max_it, verbose)
+            return self._finish_solve(count, start_time, output_base_name, verbose, save)
         self._sync_params()
         H = self._handle
         H.upload(self.Var, self.VarOld, self.Ff)
         H.reset_counters()
-        crit, max_it = self._crit(), int(self.settings.max_iterations)
         count, converged = 0, False
         try:
             while not converged and count < max_it:
@@ -266,6 +291,9 @@ class CFDSolver:
                 self.last_sweeps, self.total_sweeps = st['last_sweeps'], st['total_sweeps']
         finally:
             H.download(self.Var, self.VarOld, self.Ff, self.residual)
+        return self._finish_solve(count, start_time, output_base_name, verbose, save)
+
+    def _finish_solve(self, count, start_time, output_base_name, verbose, save):
         end_time = time.time()
         if verbose:
             print(f"\n\nSimulation completed in {end_time - start_time:.2f} seconds")
@@ -273,6 +301,34 @@ class CFDSolver:
         if save:
             self._save_results(output_base_name)
         return count, end_time - start_time
+
+    # ---- grids small enough for one CTA (the 10x10 coarse stage): the whole solve() in one launch ----
+    resident_solve = True        # set False to force the whole-GPU kernels on a small grid
+
+    def _fits_one_cta(self) -> bool:
+        order = getattr(self.settings, 'sweep_order', 'GS_LEX')
+        if not self.resident_solve or (order.upper() if isinstance(order, str) else order) not in ('GS_LEX', capi.ORDERS['GS_LEX']):
+            return False
+        return fits_one_cta(self.mesh.nx, self.mesh.ny)
+
+    def _solve_resident(self, crit, max_it, verbose) -> int:
+        """solve() through srcfd_coarse_solve_batch (one case): same iterates, same history cadence; the
+        every-100-iterations lines are printed once the launch is back."""
+        st = (self.Var[None], self.VarOld[None], self.Ff[None])
+        r = capi.coarse_solve_batch([self._params()], max_it, crit, hist_cap=max_it // 100 + 1, state=st)
+        self.residual[:] = r['residual'][0]
+        self.last_sweeps, self.total_sweeps = r['last_sweeps'][0], r['total_sweeps'][0]
+        for i, row in enumerate(r['hist'][0]):
+            if verbose:
+                print(f"{100 * (i + 1)}\t{row[0]:.6e}\t{row[1]:.6e}\t{row[2]:.6e}")
+            for k, n in enumerate('uvp'):
+                self.residual_history[n].append(row[k])
+        if r['nan'][0]:
+            rms = r['rms'][0]
+            print("\n❌ ERROR: NaN or Inf detected in residuals!")
+            print(f"   U-residual: {rms[0]:.6e}, V-residual: {rms[1]:.6e}, P-residual: {rms[2]:.6e}")
+            raise ValueError("Solver failed: NaN/Inf in residuals")
+        return int(r['iterations'][0])
 
     # ---- output (reference layout; plots need matplotlib and are skipped when it is absent) ---
     def _group_name(self):
