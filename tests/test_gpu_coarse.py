@@ -150,3 +150,49 @@ def test_ensemble_coarse_stage_matches_per_case_workflow():
         ref = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=400, bc=E._case_bc(spec), save=False)
         for n in 'uvp':
             assert f[n].shape == (10, 10) and np.array_equal(f[n], ref[n])
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_reference_golden_outputs_at_the_reference_budget(golden_dir):
+    """BASELINE config 2 stage A on the GPU: the reference's own committed outputs -- the table in
+    outputs/bfs_Re400_centerline.dat and the u/v/p vectors of the 18 coarse result .h5 files
+    (tests/golden/reference_outputs.npz) -- reproduced by 100 000-iteration 10x10 solves, all cases in one launch.
+    Tolerances as in tests/test_oracle_golden.py (the file's 6-decimal rounding; the reference's run-to-run scatter)."""
+    import os
+    from srcfd import _capi as capi
+    gr = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    # "bfs code given by sir.py":856-861 sets case_type after the constructor: first BC pass without the inlet
+    init = O.OracleSolver(O.bfs_case(10, 10), bfs_at_init=False)
+    sir = capi.coarse_solve_batch([_params(O.bfs_case(10, 10))], 100000, (1e-6,) * 3,
+                                  state=(init.Var[None].copy(), init.VarOld[None].copy(), init.Ff[None].copy()))
+    dat = gr["centerline_dat"]
+    assert np.max(np.abs(sir["Var"][0, 0, 10 // 2, 1:-1] - dat[:, 1])) <= 5.01e-7
+    assert np.max(np.abs(sir["Var"][0, 1, 1:-1, 10 // 2] - dat[:, 3])) <= 5.01e-7
+
+    names = list(gr["coarse_names"])
+    cases, idx = [O.bfs_case(10, 10)], [None]
+    for i, nm in enumerate(names):
+        if "bfs" in nm:
+            continue
+        c = O.Case(nx=10, ny=10, Re=1000.0 if "Re1000" in nm else 800.0, dt=1e-3, scheme="QUICK")
+        if nm.startswith("07-11"):
+            c.bc_values[0][3] = 1.0
+        cases.append(c); idx.append(i)
+    r = capi.coarse_solve_batch([_params(c) for c in cases], 100000, (1e-6,) * 3)
+    assert not r["nan"].any()
+    flat = lambda i: [r["Var"][i, k, 1:-1, 1:-1].T.flatten() for k in range(3)]
+    mine, hits = flat(0), 0
+    for i, nm in enumerate(names):
+        if "bfs_coarse_Re400" in nm:
+            g = gr[f"coarse_{i}"]; hits += 1
+            assert _rel(mine[0], g[0]) <= 1e-8 and _rel(mine[1], g[1]) <= 1e-8 and _rel(mine[2], g[2]) <= 5e-6, nm
+    assert hits == 14
+    for j in range(1, len(cases)):
+        g, m = gr[f"coarse_{idx[j]}"], flat(j)
+        pd, pg = m[2] - m[2].mean(), g[2] - g[2].mean()
+        tol = 1e-7 if r["iterations"][j] == 100000 else 1e-3
+        assert _rel(m[0], g[0]) <= tol and _rel(m[1], g[1]) <= tol and _rel(pd, pg) <= tol, names[idx[j]]
+    assert len(cases) == 5
