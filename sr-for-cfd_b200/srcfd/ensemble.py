@@ -94,10 +94,23 @@ def coarse_stage(cases: Sequence[CaseSpec], device: int = 0, lr_dim: int = 10, m
     return [{n: r['Var'][i, k, 1:-1, 1:-1].T.copy() for k, n in enumerate('uvp')} for i in range(len(cases))]
 
 
+def warm_start_fields(spec: CaseSpec, sr_files: dict, coarse: Optional[dict] = None) -> np.ndarray:
+    """Steps 1-2 of the per-case workflow (coarse solve unless given, then ml_super_resolution): the (3, ny, nx)
+    float32 initial guess of one case."""
+    from . import bfs, ldc
+    wf = (bfs if spec.kind == "bfs" else ldc)._wf
+    if coarse is None:
+        coarse = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=sr_files.get("coarse_iterations", 2000),
+                                          bc=_case_bc(spec), save=False)
+    kw = dict(use_aspect_ratio_correction=True, lx=10.0, ly=3.0) if spec.kind == "bfs" else {}
+    hr = wf.ml_super_resolution(coarse, 10, spec.nx, sr_files["stats"], sr_files["encoder"], sr_files["decoder"], **kw)
+    return np.stack([np.asarray(hr[c], dtype=np.float32) for c in "uvp"])
+
+
 def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optional[dict] = None, keep_fields=True,
-             coarse: Optional[dict] = None) -> CaseResult:
+             coarse: Optional[dict] = None, warm: Optional[np.ndarray] = None) -> CaseResult:
     """Coarse solve -> SR warm start -> fine solve for one case on one GPU (the reference's per-case workflow).
-    `coarse`: this case's coarse fields when coarse_stage already produced them."""
+    `coarse`: this case's coarse fields when coarse_stage already produced them; `warm`: its finished initial guess."""
     from . import bfs, ldc
     mod = bfs if spec.kind == "bfs" else ldc
     wf = mod._wf
@@ -106,14 +119,11 @@ def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optio
     solver = wf._make_solver(spec.Re, spec.nx, spec.ny, *wf._defaults(None, None, None, None)[:2], None,
                              spec.max_iterations, bc, 1.0, 2.0, 1.0, *wf._defaults(None, None, None, None)[2:], None,
                              device=device, max_ctas=max_ctas)
-    if spec.warm_start and sr_files is not None:
-        if coarse is None:
-            coarse = wf.run_coarse_simulation(Re=spec.Re, lr_dim=10, max_iterations=sr_files.get("coarse_iterations", 2000),
-                                              bc=bc, save=False)
-        kw = dict(use_aspect_ratio_correction=True, lx=10.0, ly=3.0) if spec.kind == "bfs" else {}
-        hr = wf.ml_super_resolution(coarse, 10, spec.nx, sr_files["stats"], sr_files["encoder"], sr_files["decoder"], **kw)
+    if warm is None and spec.warm_start and sr_files is not None:
+        warm = warm_start_fields(spec, sr_files, coarse)
+    if warm is not None:
         solver._sync_params()
-        solver._handle.set_fields(np.stack([np.asarray(hr[c], dtype=np.float32) for c in "uvp"]))
+        solver._handle.set_fields(warm)
         solver._handle.download(solver.Var, solver.VarOld, solver.Ff)
     n, _ = solver.solve("ensemble", verbose=False, save=False)
     st = solver._handle.status()
@@ -122,18 +132,29 @@ def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optio
                       [int(x) for x in solver.total_sweeps], [float(x) for x in st["rms"]], fields)
 
 
-def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, num_sms: int = 148,
-              runner: Callable = run_case, **kw) -> List[CaseResult]:
-    """Run this rank's cases, `concurrency` at a time, each with 1/concurrency of the SMs."""
+def warm_stage(cases: Sequence[CaseSpec], sr_files: dict, device: int = 0) -> List[Optional[np.ndarray]]:
+    """Warm start of a whole share of cases: ONE launch for every coarse solve (coarse_stage), then the SR passes back
+    to back on the calling thread (an Encoder/Decoder handle serves one caller at a time)."""
+    out: List[Optional[np.ndarray]] = [None] * len(cases)
+    warm = [i for i, c in enumerate(cases) if c.warm_start]
+    coarse = coarse_stage([cases[i] for i in warm], device, 10, sr_files.get("coarse_iterations", 2000))
+    for i, f in zip(warm, coarse):
+        out[i] = warm_start_fields(cases[i], sr_files, f)
+    return out
+
+
+def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 4, num_sms: int = 148,
+              runner: Callable = run_case, warm_fields: Optional[List] = None, **kw) -> List[CaseResult]:
+    """Run this rank's cases, `concurrency` at a time, each with 1/concurrency of the SMs.  `warm_fields`: the cases'
+    initial guesses when warm_stage ran already."""
     results: List[Optional[CaseResult]] = [None] * len(cases)
     lock, nxt = threading.Lock(), [0]
     max_ctas = max(1, num_sms // max(1, concurrency)) if concurrency > 1 else 0
     sr_files = kw.get("sr_files")
-    coarse = [None] * len(cases)
-    if runner is run_case and sr_files is not None and any(c.warm_start for c in cases):
-        warm = [i for i, c in enumerate(cases) if c.warm_start]
-        for i, f in zip(warm, coarse_stage([cases[i] for i in warm], device, 10, sr_files.get("coarse_iterations", 2000))):
-            coarse[i] = f
+    if warm_fields is None:
+        warm_fields = [None] * len(cases)
+        if runner is run_case and sr_files is not None and any(c.warm_start for c in cases):
+            warm_fields = warm_stage(cases, sr_files, device)      # the workers below only run fine solves
 
     def worker():
         while True:
@@ -142,7 +163,7 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, 
                 nxt[0] += 1
             if i >= len(cases):
                 return
-            extra = dict(coarse=coarse[i]) if coarse[i] is not None else {}
+            extra = dict(warm=warm_fields[i]) if warm_fields[i] is not None else {}
             results[i] = runner(cases[i], device=device, max_ctas=max_ctas, **extra, **kw)
 
     threads = [threading.Thread(target=worker) for _ in range(max(1, min(concurrency, len(cases))))]
@@ -153,7 +174,7 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 2, 
     return [r for r in results if r is not None]
 
 
-def run_ensemble(cases: Sequence[CaseSpec], concurrency: int = 2, runner: Callable = run_case, dist=None,
+def run_ensemble(cases: Sequence[CaseSpec], concurrency: int = 4, runner: Callable = run_case, dist=None,
                  device: Optional[int] = None, **kw) -> Optional[List[CaseResult]]:
     """Shard `cases` over the ranks of an initialised torch.distributed group (or run them all when there is
     none) and gather every CaseResult on rank 0 (other ranks return None).  No collective on the data path."""
