@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "cell_ops.cuh"
+#include "inner_gs2.cuh"
 
 namespace srcfd {
 
@@ -48,17 +49,35 @@ struct CoarseOut {
 struct CoarseShared {
     int hit;
     int flag;
-    double last_rms;
+    double last_v;           // sum of R^2 of the last sweep the reducer looked at
+    double v_hit;            // smallest sum whose rms is NOT below the tolerance (see coarse_threshold)
     double red[3][32];
 };
 
+// The break test of LDC.py:266-268 is  sqrt(sum / (Nx*Ny)) < tolerance.  Division by a positive constant and sqrt are
+// correctly rounded, hence monotone, so the test is EXACTLY  sum < T  with T the smallest non-negative double whose rms
+// is >= tolerance -- found once per case by bisection on the bit pattern.  That takes a division and a square root (two
+// long dependent chains) off every sweep's critical path.
+__device__ inline double coarse_threshold(double tol, double ncells) {
+    unsigned long long lo = 0ull, hi = 0x7ff0000000000000ull;          // +0 .. +inf
+    if (!(sqrt(__longlong_as_double((long long)hi) / ncells) >= tol)) return 0.0;   // NaN tolerance: never below
+    while (lo < hi) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (sqrt(__longlong_as_double((long long)mid) / ncells) >= tol) hi = mid; else lo = mid + 1;
+    }
+    return __longlong_as_double((long long)lo);
+}
+
 // `limit` pipelined sweeps of plane k.  Returns the 1-based index of the first sweep whose rms met the tolerance
 // (check only), 0 when none did.  Block-uniform; ends with every thread past a barrier.
+// A worker's active steps are consecutive (from t_first on it updates one cell per step), so its position inside the
+// sweep (r), the sweep (s) and the ring slot advance by counters: no division in the step loop.  The loop-invariant
+// divisors go through the exact reciprocal sequence of inner_gs2.cuh (same bits as '/', a third of the latency).
 template <int OP>
 __device__ __forceinline__ int coarse_sweeps(double* __restrict__ Var, const double* __restrict__ VarOld,
                                              const double* __restrict__ Ff, const double* __restrict__ rhs,
                                              double* __restrict__ part, CoarseShared* sh, int k, int limit, bool check,
-                                             const Consts& K, double tol, int ring, int stride) {
+                                             const Consts& K, const Gs2Div& D, double tol, int ring, int stride) {
     constexpr int L = (OP == OP_QUICK) ? 3 : 2;
     const int nx = K.nx, ny = K.ny, pitch = K.pitch;
     const int P = (int)K.plane;
@@ -72,60 +91,62 @@ __device__ __forceinline__ int coarse_sweeps(double* __restrict__ Var, const dou
     const int t_end = L * (limit - 1) + tail + (check ? 1 : 0);
     double* Vk = Var + k * P;
     const double* Ok = VarOld + k * P;
+    const int t_first = worker ? i0 + L * m : 0x7fffffff;
+    const int c0 = (i0 + 1) * pitch + L * m + 1;
+    const int jleft = ny - L * m;             // cells of this thread inside the row: r < jleft
+    // QUICK second neighbours on the flat buffer (SURVEY.md hazard H4): a negative index wraps to the other end of its
+    // axis, one past the end runs on into the next row / plane
+    const int off_im2 = ((i0 - 1 < 0) ? i0 - 1 + nx + 2 : i0 - 1) * pitch - (i0 + 1) * pitch;
+    int r = 0, s = 0, slot = 0;               // worker: position in the sweep, sweep, ring slot
+    int next_t = tail + 1, s_r = 0, slot_r = 0;   // reducer: step at which sweep s_r is complete
     double acc = 0.0;
     if (tid == 0) sh->hit = 0;
     __syncthreads();
+    const double v_hit = sh->v_hit;
+    int found = 0;
     for (int t = 0; t <= t_end; ++t) {
-        if (check && sh->hit) break;
-        if (worker) {
-            const int rel = t - i0;
-            if (rel >= 0) {
-                const int q = rel / L, r = rel - q * L;
-                const int s = q - m;
-                if (s >= 0 && s < limit) {
+        if (t >= t_first && s < limit) {
+            if (r == 0) acc = 0.0;
+            if (r < jleft) {
+                const int c = c0 + r;
+                const double cc = Vk[c], ip = Vk[c + pitch], im = Vk[c - pitch], jp = Vk[c + 1], jm = Vk[c - 1];
+                double R, nv;
+                if (OP == OP_PRESSURE) {
+                    nv = pressure_cell2(cc, ip, im, jp, jm, rhs[c], K, D, R);
+                } else if (OP == OP_UPWIND) {
+                    nv = upwind_cell2(cc, ip, im, jp, jm, Ok[c], Ff[c], Ff[P + c], Ff[2 * P + c], Ff[3 * P + c], K, D, R);
+                } else {
                     const int j0 = L * m + r;
-                    if (r == 0) acc = 0.0;
-                    if (j0 < ny) {
-                        const int c = (i0 + 1) * pitch + j0 + 1;
-                        const double cc = Vk[c], ip = Vk[c + pitch], im = Vk[c - pitch], jp = Vk[c + 1], jm = Vk[c - 1];
-                        double R, nv;
-                        if (OP == OP_PRESSURE) {
-                            nv = pressure_cell(cc, ip, im, jp, jm, rhs[c], K, R);
-                        } else if (OP == OP_UPWIND) {
-                            nv = upwind_cell(cc, ip, im, jp, jm, Ok[c], Ff[c], Ff[P + c], Ff[2 * P + c], Ff[3 * P + c], K, R);
-                        } else {
-                            // second neighbours on the flat buffer (SURVEY.md hazard H4): a negative index wraps to the
-                            // other end of its axis, one past the end runs on into the next row / plane
-                            const int rm2 = (i0 - 1 < 0) ? i0 - 1 + nx + 2 : i0 - 1;
-                            const int cm2 = (j0 - 1 < 0) ? j0 - 1 + ny + 2 : j0 - 1;
-                            const double ip2 = Vk[c + 2 * pitch], im2 = Vk[rm2 * pitch + j0 + 1];
-                            const double jp2 = Vk[c + 2], jm2 = Vk[(i0 + 1) * pitch + cm2];
-                            nv = quick_cell(cc, ip, im, jp, jm, ip2, im2, jp2, jm2, Ok[c], Ff[c], Ff[P + c], Ff[2 * P + c],
-                                            Ff[3 * P + c], K, R);
-                        }
-                        Vk[c] = nv;
-                        acc += R * R;
-                    }
-                    if (check && r == L - 1) part[(s % ring) * stride + tid] = acc;
+                    const int cm2 = (j0 - 1 < 0) ? j0 - 1 + ny + 2 : j0 - 1;
+                    const double ip2 = Vk[c + 2 * pitch], im2 = Vk[c + off_im2];
+                    const double jp2 = Vk[c + 2], jm2 = Vk[(i0 + 1) * pitch + cm2];
+                    nv = quick_cell2(cc, ip, im, jp, jm, ip2, im2, jp2, jm2, Ok[c], Ff[c], Ff[P + c], Ff[2 * P + c],
+                                     Ff[3 * P + c], K, D, R);
                 }
+                Vk[c] = nv;
+                acc += R * R;
             }
-        } else if (reducer && check) {
-            const int e = t - 1 - tail;
-            if (e >= 0 && e % L == 0 && e / L < limit) {
-                const int s = e / L, lane = tid & 31;
-                const double* ps = part + (s % ring) * stride;
-                double v = 0.0;
-                for (int w = lane; w < nwork; w += 32) v += ps[w];
+            if (++r == L) {
+                if (check) part[slot * stride + tid] = acc;
+                r = 0; ++s;
+                if (++slot == ring) slot = 0;
+            }
+        } else if (reducer && check && t == next_t && s_r < limit) {
+            const int lane = tid & 31;
+            const double* ps = part + slot_r * stride;
+            double v = 0.0;
+            for (int w = lane; w < nwork; w += 32) v += ps[w];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) {
-                    const double rms = sqrt(v / (double)((long long)nx * (long long)ny));
-                    sh->last_rms = rms;
-                    if (rms < tol) sh->hit = s + 1;
-                }
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            found = v < v_hit;
+            if (lane == 0) {
+                sh->last_v = v;
+                if (found) sh->hit = s_r + 1;
             }
+            next_t += L; ++s_r;
+            if (++slot_r == ring) slot_r = 0;
         }
-        __syncthreads();
+        if (__syncthreads_or(found)) break;      // the step barrier also carries the reducer's verdict
     }
     __syncthreads();
     const int hit = sh->hit;
@@ -134,24 +155,29 @@ __device__ __forceinline__ int coarse_sweeps(double* __restrict__ Var, const dou
 }
 
 // One inner solve (LDC.py:248-314): <= inner_max sweeps, stop after the first whose rms < tolerance.
+// Guess policy: a run that meets the tolerance BEFORE its limit costs a restore and a full replay, one that falls
+// short only a short follow-up segment.  Long solves (>= 32 sweeps, whose counts drift down by a sweep every few outer
+// iterations) therefore aim 2 sweeps below the previous count and finish in segments of 4, 8, 16, ... sweeps.
 template <int OP>
 __device__ int coarse_inner(double* Var, const double* VarOld, const double* Ff, const double* rhs, double* snap,
-                            double* part, CoarseShared* sh, int k, int& guess, const Consts& K, double tol, int maxs,
-                            int ring, int stride) {
+                            double* part, CoarseShared* sh, int k, int& guess, const Consts& K, const Gs2Div& D,
+                            double tol, int maxs, int ring, int stride) {
     const int ncell = K.nx * K.ny, P = (int)K.plane;
     double* Vk = Var + k * P;
-    int done = 0, g = guess < 1 ? 1 : guess;
+    const bool under = guess >= 32;
+    int done = 0, g = guess < 1 ? 1 : (under ? guess - 2 : guess), follow = 4;
     while (true) {
         for (int idx = threadIdx.x; idx < ncell; idx += blockDim.x) {
             const int c = (idx / K.ny + 1) * K.pitch + idx % K.ny + 1;
             snap[c] = Vk[c];
         }
         const int limit = g < maxs - done ? g : maxs - done;
-        const int hit = coarse_sweeps<OP>(Var, VarOld, Ff, rhs, part, sh, k, limit, true, K, tol, ring, stride);
+        const int hit = coarse_sweeps<OP>(Var, VarOld, Ff, rhs, part, sh, k, limit, true, K, D, tol, ring, stride);
         if (hit == 0) {
             done += limit;
             if (done >= maxs) break;
-            g = limit / 4 < 4 ? 4 : limit / 4;
+            if (under) { g = follow; follow *= 2; }
+            else g = limit / 4 < 4 ? 4 : limit / 4;
             continue;
         }
         if (hit < limit) {
@@ -159,7 +185,7 @@ __device__ int coarse_inner(double* Var, const double* VarOld, const double* Ff,
                 const int c = (idx / K.ny + 1) * K.pitch + idx % K.ny + 1;
                 Vk[c] = snap[c];
             }
-            coarse_sweeps<OP>(Var, VarOld, Ff, rhs, part, sh, k, hit, false, K, tol, ring, stride);
+            coarse_sweeps<OP>(Var, VarOld, Ff, rhs, part, sh, k, hit, false, K, D, tol, ring, stride);
         }
         done += hit;
         break;
@@ -267,15 +293,19 @@ __global__ void __launch_bounds__(640, 1) k_coarse_solve(const CoarseCase* __res
     int last_n[3] = {0, 0, 0};
     const double tol = cs_sh.inner_tol;
     const int maxs = cs_sh.inner_max;
+    if (tid == 0) { sh.v_hit = coarse_threshold(tol, (double)((long long)K.nx * (long long)K.ny)); sh.last_v = 0.0; }
+    __syncthreads();
+    Gs2Div D;
+    D.dx2 = make_invdiv(K.dx2); D.dy2 = make_invdiv(K.dy2); D.apd = make_invdiv(K.ap_d);
     while (!converged && count < cs_sh.max_iterations) {
         count += 1;
         // _implicit_solve (LDC.py:432-467 / BFS.py:622-673)
         for (int k = 0; k < 2; ++k) {
             int n;
-            if (cs_sh.scheme == 1) n = coarse_inner<OP_QUICK>(Var, VarOld, Ff, rhs, snap, part, &sh, k, guess[k], K, tol, maxs, ring, stride);
-            else                   n = coarse_inner<OP_UPWIND>(Var, VarOld, Ff, rhs, snap, part, &sh, k, guess[k], K, tol, maxs, ring, stride);
+            if (cs_sh.scheme == 1) n = coarse_inner<OP_QUICK>(Var, VarOld, Ff, rhs, snap, part, &sh, k, guess[k], K, D, tol, maxs, ring, stride);
+            else                   n = coarse_inner<OP_UPWIND>(Var, VarOld, Ff, rhs, snap, part, &sh, k, guess[k], K, D, tol, maxs, ring, stride);
             total[k] += n; last_n[k] = n;
-            inner_rms[k] = sh.last_rms;
+            inner_rms[k] = sqrt(sh.last_v / (double)((long long)K.nx * (long long)K.ny));
             if (cs_sh.relax_enabled) {
                 const double a = cs_sh.relax[k];
                 for (int idx = tid; idx < ncell; idx += nth) {
@@ -288,9 +318,9 @@ __global__ void __launch_bounds__(640, 1) k_coarse_solve(const CoarseCase* __res
         }
         coarse_interpolate(Var, Ff, rhs, K);
         {
-            const int n = coarse_inner<OP_PRESSURE>(Var, VarOld, Ff, rhs, snap, part, &sh, 2, guess[2], K, tol, maxs, ring, stride);
+            const int n = coarse_inner<OP_PRESSURE>(Var, VarOld, Ff, rhs, snap, part, &sh, 2, guess[2], K, D, tol, maxs, ring, stride);
             total[2] += n; last_n[2] = n;
-            inner_rms[2] = sh.last_rms;
+            inner_rms[2] = sqrt(sh.last_v / (double)((long long)K.nx * (long long)K.ny));
             if (cs_sh.relax_enabled) {
                 const double a = cs_sh.relax[2];
                 for (int idx = tid; idx < ncell; idx += nth) {
