@@ -126,10 +126,9 @@ def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optio
         solver._handle.set_fields(warm)
         solver._handle.download(solver.Var, solver.VarOld, solver.Ff)
     n, _ = solver.solve("ensemble", verbose=False, save=False)
-    st = solver._handle.status()
     fields = np.stack([solver.Var[k, 1:-1, 1:-1].T for k in range(3)]) if keep_fields else None
-    return CaseResult(spec.label(), -1, int(n), bool(st["converged"]), time.time() - t0,
-                      [int(x) for x in solver.total_sweeps], [float(x) for x in st["rms"]], fields)
+    return CaseResult(spec.label(), -1, int(n), bool(solver.converged), time.time() - t0,
+                      [int(x) for x in solver.total_sweeps], [float(x) for x in solver.last_rms], fields)
 
 
 def warm_stage(cases: Sequence[CaseSpec], sr_files: dict, device: int = 0) -> List[Optional[np.ndarray]]:

@@ -186,6 +186,7 @@ class CFDSolver:
         self.residual_history = {'u': [], 'v': [], 'p': []}
         self.last_sweeps = np.zeros(3, dtype=np.int64)
         self.total_sweeps = np.zeros(3, dtype=np.int64)
+        self.converged, self.last_rms = False, np.zeros(3)      # verdict and rms triplet of the last solve()
         self._handle = capi.Handle(self._params())
         self._initialize_fields()
 
@@ -289,6 +290,7 @@ class CFDSolver:
                     for k, n in enumerate('uvp'):
                         self.residual_history[n].append(st['rms'][k])
                 self.last_sweeps, self.total_sweeps = st['last_sweeps'], st['total_sweeps']
+                self.converged, self.last_rms = bool(converged), np.array(st['rms'], dtype=np.float64)
         finally:
             H.download(self.Var, self.VarOld, self.Ff, self.residual)
         return self._finish_solve(count, start_time, output_base_name, verbose, save)
@@ -317,6 +319,7 @@ class CFDSolver:
         st = (self.Var[None], self.VarOld[None], self.Ff[None])
         r = capi.coarse_solve_batch([self._params()], max_it, crit, hist_cap=max_it // 100 + 1, state=st)
         self.residual[:] = r['residual'][0]
+        self.converged, self.last_rms = bool(r['converged'][0]), r['rms'][0].copy()
         self.last_sweeps, self.total_sweeps = r['last_sweeps'][0], r['total_sweeps'][0]
         for i, row in enumerate(r['hist'][0]):
             if verbose:
