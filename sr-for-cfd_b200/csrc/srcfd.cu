@@ -581,6 +581,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
         Gs3Args g3;
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
+        g3.k1_max = getenv("SRCFD_K1MAX") ? atoi(getenv("SRCFD_K1MAX")) : 128;
         g3.s.prog = h->trace ? h->prog : nullptr;      // this kernel has no progress flags: non-null only asks it to count polls
         g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * h->gs3_stride; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
         g3.skip_idle = getenv("SRCFD_SKIP_IDLE") ? atoi(getenv("SRCFD_SKIP_IDLE")) : 1;
