@@ -417,3 +417,21 @@ def test_ensemble_concurrent_cases_match_sequential():
         assert np.array_equal(a.fields, b.fields)
     o = O.OracleSolver(O.bfs_case(48, 40)); o.solve(6)
     assert np.array_equal(par[2].fields, np.stack([o.Var[k, 1:-1, 1:-1].T for k in range(3)]))
+
+
+@pytest.mark.parametrize("nx,ny,Re,its", [(24, 20, 100.0, 1500), (40, 36, 400.0, 600)])
+def test_long_run_with_drifting_sweep_counts_kernel_path(nx, ny, Re, its):
+    """The converging regime on the whole-GPU kernels (resident one-CTA path switched off): pressure sweep counts fall
+    from the cap through the one-sweep-group range of k_solve_gs3 (runs aimed 2 sweeps past the guess and finished from
+    the boundary ring, follow-up runs, reruns) -- every outer iteration's break must land on the reference's sweep."""
+    from srcfd import ldc
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=nx, ny=ny), ldc.FluidProperties(Re=Re),
+                      ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=its), ldc.BoundaryConditions())
+    s.resident_solve = False
+    n, _ = s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.Case(nx=nx, ny=ny, Re=Re, dt=1e-3, scheme="QUICK"))
+    m, rms, hist = o.solve(its)
+    assert n == m
+    assert list(s.total_sweeps) == o.total_sweeps.tolist()
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.VarOld, o.VarOld) and np.array_equal(s.Ff, o.Ff)
+    assert 3 * its < o.total_sweeps[2] < 1000 * its          # neither at the cap throughout nor trivially short
