@@ -196,3 +196,21 @@ def test_reference_golden_outputs_at_the_reference_budget(golden_dir):
         tol = 1e-7 if r["iterations"][j] == 100000 else 1e-3
         assert _rel(m[0], g[0]) <= tol and _rel(m[1], g[1]) <= tol and _rel(pd, pg) <= tol, names[idx[j]]
     assert len(cases) == 5
+
+
+def test_ensemble_warm_stage_then_concurrent_fine_solves(golden_dir):
+    """run_local with SR files: one batched coarse launch + SR passes up front, fine solves concurrently -- the same
+    fields as the per-case workflow (coarse solve, SR and fine solve one case after the other)."""
+    import os
+    from srcfd import bfs, ensemble as E, ldc, sr
+    bfs._wf.verbose = ldc._wf.verbose = False
+    files = dict(stats=os.path.join(golden_dir, "stats_10to400_multiBC.txt"),
+                 encoder=sr.load_model(os.path.join(golden_dir, "encoder10_multiBC.h5")),
+                 decoder=sr.synthetic_decoder(seed=0), coarse_iterations=300)
+    cases = [E.CaseSpec("ldc", 100.0, 400, 400, 3), E.CaseSpec("bfs", 400.0, 400, 400, 3), E.CaseSpec("ldc2", 500.0, 400, 400, 3)]
+    seq = [E.run_case(c, sr_files=files) for c in cases]
+    par = E.run_local(cases, concurrency=3, sr_files=files)
+    for a, b in zip(seq, par):
+        assert a.label == b.label and a.iterations == b.iterations == 3 and a.total_sweeps == b.total_sweeps
+        assert np.array_equal(a.fields, b.fields)
+        assert np.isfinite(b.fields).all() and np.abs(b.fields).max() > 0
