@@ -298,7 +298,15 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         h->launches += 2;
         for (int l = 1; l <= 4; ++l)
             if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
-        k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->fcw, out_dev, B, 400, 400);
+        const char* ftc = getenv("SRCFD_FINAL_TC");                 // 0: the CUDA-core tile kernel (read per call: tests toggle it)
+        if (!(ftc && atoi(ftc) == 0)) {
+            srtc::FinalW fw;
+            memcpy(fw.w, h->fcw.w, sizeof(fw.w)); fw.b = h->fcw.b;
+            srtc::k_conv3x3_c8_final_tc<<<dim3((400 + 127) / 128, (400 + srtc::FT_R - 1) / srtc::FT_R, B), 128, srtc::FT_SMEM, h->stream>>>(
+                h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
+        } else {
+            k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->fcw, out_dev, B, 400, 400);
+        }
         h->launches += 1;
     }
     SRCK(cudaGetLastError());

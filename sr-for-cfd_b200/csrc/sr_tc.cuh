@@ -192,4 +192,115 @@ __global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __res
         out[t] = __bfloat162float(in[t]);
 }
 
+// ---- final Conv2D(1, 3x3, 'same', linear) over the 8-channel bf16 activation, on the tensor cores ------------------
+// With Cin = 8 one pixel is exactly one 16-byte K-chunk, so the staged input rows (pixel-contiguous, 16 B per pixel)
+// ARE the canonical K-major SWIZZLE_NONE operand: rows r = 128 consecutive pixels (8-row groups SBO = 128 B apart),
+// and the operand of tap (dy, dx) for output row yy is the same buffer at byte offset (yy + dy) * ROWB + dx * 16 --
+// an implicit GEMM with no im2col at all.  One tcgen05.mma consumes K = 16 = two chunks LBO apart: LBO = ROWB pairs
+// the taps (dy, dx) and (dy + 1, dx); the odd third row is paired with a zero-weight chunk (a zeroed extra row).
+// N = 16 (the smallest N for M = 128) with only column 0 carrying weights; one accumulator (16 TMEM columns) per
+// output row, R rows per CTA: 6 MMAs per row.  Epilogue: thread = pixel reads column 0 of each accumulator, adds the
+// bias and stores fp32 (128 B per warp and row).
+struct FinalW { float w[72]; float b; };
+constexpr int FT_R = 8;                                  // output rows per CTA
+constexpr int FT_PX = 130;                               // staged pixels per row (128 + halo)
+constexpr int FT_ROWB = FT_PX * 16;                      // bytes per staged row
+constexpr int FT_ROWS = FT_R + 3;                        // halo above / below + one zero row for the padded K-chunk
+constexpr size_t FT_SMEM = (size_t)FT_ROWS * FT_ROWB + 6 * 512;
+
+__global__ void __launch_bounds__(128) k_conv3x3_c8_final_tc(const __nv_bfloat16* __restrict__ in, const FinalW fw, float* __restrict__ out,
+                                                             int H, int Wd, int* err) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sA = smem_raw;
+    unsigned char* sB = smem_raw + (size_t)FT_ROWS * FT_ROWB;          // 6 blocks of 16 x 16 bf16 (512 B each)
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, y0 = blockIdx.y * FT_R, x0 = blockIdx.x * 128;
+    constexpr int NCOL = 16 * FT_R;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(NCOL) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- stage the input rows (zeros outside the image and in the extra row): all loads in flight, then the stores
+    const __nv_bfloat16* src = in + (long long)b * H * Wd * 8;
+    constexpr int NCH = FT_ROWS * FT_PX, PER = (NCH + 127) / 128;
+    uint4 v[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int c = tid + q * 128;
+        const int sy = c / FT_PX, px = c - sy * FT_PX;
+        const int y = y0 - 1 + sy, x = x0 - 1 + px;
+        v[q] = make_uint4(0, 0, 0, 0);
+        if (c < NCH && sy < FT_R + 2 && y >= 0 && y < H && x >= 0 && x < Wd)
+            v[q] = __ldg(reinterpret_cast<const uint4*>(src + ((long long)y * Wd + x) * 8));
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int c = tid + q * 128;
+        if (c < NCH) *reinterpret_cast<uint4*>(sA + (size_t)c * 16) = v[q];
+    }
+    // ---- weights: block (dx, half): chunk 0 = tap (2*half, dx), chunk 1 = tap (2*half + 1, dx) or zeros; row n = 0 only
+    for (int c = tid; c < 6 * 512 / 16; c += 128) *reinterpret_cast<uint4*>(sB + (size_t)c * 16) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (tid < 6 * 2) {
+        const int blk = tid >> 1, kc = tid & 1, dx = blk >> 1, half = blk & 1, dy = 2 * half + kc;
+        if (dy < 3) {
+            __nv_bfloat16 o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16(fw.w[(dy * 3 + dx) * 8 + e]);
+            *reinterpret_cast<uint4*>(sB + (size_t)blk * 512 + kc * 256) = *reinterpret_cast<const uint4*>(o);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, 16);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+        for (int yy = 0; yy < FT_R; ++yy) {
+#pragma unroll
+            for (int blk = 0; blk < 6; ++blk) {
+                const int dx = blk >> 1, half = blk & 1;
+                const uint64_t ad = make_smem_desc(a0 + (uint32_t)(yy + 2 * half) * FT_ROWB + (uint32_t)dx * 16, FT_ROWB, 128);
+                const uint64_t bd = make_smem_desc(b0 + (uint32_t)blk * 512, 256, 128);
+                umma_bf16(tmem + 16u * yy, ad, bd, idesc, blk > 0 ? 1u : 0u);
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        }
+        if (!done && lane == 0) atomicExch(err, 1);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t acc[FT_R];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int yy = 0; yy < FT_R; ++yy)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(acc[yy]) : "r"(taddr + 16u * yy) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int x = x0 + tid;
+    if (x < Wd) {
+#pragma unroll
+        for (int yy = 0; yy < FT_R; ++yy)
+            if (y0 + yy < H) out[((long long)b * H + y0 + yy) * Wd + x] = __uint_as_float(acc[yy]) + fw.b;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOL) : "memory");
+}
+
 }  // namespace srtc

@@ -96,3 +96,30 @@ def test_decoder_bf16_tensor_core_path():
     ref = S.decoder_forward(z, dec.weights)
     scale = np.abs(ref).max()
     assert np.abs(out - ref).max() <= 3e-2 * scale, (np.abs(out - ref).max(), scale)
+
+
+def test_final_conv_on_tensor_cores_matches_cuda_core_kernel():
+    """bf16 path: the tcgen05 implicit-GEMM final 3x3 conv against the CUDA-core tile kernel on the same bf16
+    activation.  The only difference is the bf16 rounding of the 72 weights (the CUDA-core kernel keeps them fp32):
+    <= 2^-8 relative per product, bounded here by sum |w| * max |activation| * 2^-8."""
+    import os
+    from srcfd import sr
+    dec = sr.synthetic_decoder(0)
+    z = np.random.default_rng(5).standard_normal((2, 50)).astype(np.float32)
+    sr.set_precision("bf16")
+    try:
+        os.environ["SRCFD_FINAL_TC"] = "0"
+        ref = dec.predict(z)
+        os.environ["SRCFD_FINAL_TC"] = "1"
+        out = dec.predict(z)
+    finally:
+        os.environ.pop("SRCFD_FINAL_TC", None)
+        sr.set_precision("fp32")
+    assert not sr.tc_error()
+    assert out.shape == ref.shape == (2, 400, 400, 1)
+    scale = np.abs(ref).max()
+    err = np.abs(out - ref)
+    assert err.max() <= 4e-3 * scale, (err.max(), scale, np.unravel_index(err.argmax(), err.shape))
+    # borders and tile seams included: rows / columns at 0, 127|128, 399 are no worse than the interior
+    for sl in (np.s_[:, 0], np.s_[:, 399], np.s_[:, :, 0], np.s_[:, :, 399], np.s_[:, :, 127:129], np.s_[:, 7:9]):
+        assert err[sl].max() <= 4e-3 * scale
