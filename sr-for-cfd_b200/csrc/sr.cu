@@ -251,7 +251,21 @@ int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* W
     const size_t smem = srtc::convT_tc_smem<KD, ND>();
     static bool attr_done[64] = {false};                 // per device: the attribute belongs to the (device, kernel) pair
     if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<KD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
-    srtc::k_convT2x2_tc<KD, ND><<<(unsigned)((M + 127) / 128), 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
+    // The kernel walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with the weights staged once per CTA.  Default: one
+    // tile per CTA.  SRCFD_TC_PERSIST=1 launches only as many CTAs as fit at once (shared memory, 512 TMEM columns per
+    // SM); measured 2.5x SLOWER at batch 1024 (20.6 vs 8.4 ms): a CTA serialises stage -> MMA -> epilogue, and without a
+    // second A buffer + accumulator the tile loop loses the overlap that CTA turnover gives for free.
+    static int per_dev[64] = {0};
+    if (!per_dev[h->dev & 63]) {
+        int occ = 0, sms = 0;
+        SRCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, srtc::k_convT2x2_tc<KD, ND>, 128, smem));
+        SRCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
+        per_dev[h->dev & 63] = std::max(1, std::min(occ, 512 / (ND < 32 ? 32 : ND))) * sms;
+    }
+    const long long ntiles = (M + 127) / 128;
+    const char* pe = getenv("SRCFD_TC_PERSIST");
+    const unsigned grid = (pe && atoi(pe) == 1) ? (unsigned)std::min<long long>(ntiles, per_dev[h->dev & 63]) : (unsigned)ntiles;
+    srtc::k_convT2x2_tc<KD, ND><<<grid, 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
     h->launches += 1;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
@@ -302,8 +316,11 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         if (!(ftc && atoi(ftc) == 0)) {
             srtc::FinalW fw;
             memcpy(fw.w, h->fcw.w, sizeof(fw.w)); fw.b = h->fcw.b;
-            srtc::k_conv3x3_c8_final_tc<<<dim3((400 + 127) / 128, (400 + srtc::FT_R - 1) / srtc::FT_R, B), 128, srtc::FT_SMEM, h->stream>>>(
-                h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
+            const int R = getenv("SRCFD_FINAL_TC_ROWS") ? atoi(getenv("SRCFD_FINAL_TC_ROWS")) : 8;
+            const dim3 grid((400 + 127) / 128, (400 + R - 1) / R, B);
+            if (R == 4) srtc::k_conv3x3_c8_final_tc<4><<<grid, 128, srtc::ft_smem<4>(), h->stream>>>(h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
+            else if (R == 16) srtc::k_conv3x3_c8_final_tc<16><<<grid, 128, srtc::ft_smem<16>(), h->stream>>>(h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
+            else srtc::k_conv3x3_c8_final_tc<8><<<grid, 128, srtc::ft_smem<8>(), h->stream>>>(h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
         } else {
             k_conv3x3_c8_final<__nv_bfloat16><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->actbf[5], h->fcw, out_dev, B, 400, 400);
         }

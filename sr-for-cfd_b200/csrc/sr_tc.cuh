@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long m0 = (long long)blockIdx.x * MT;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ND < 32 ? 32 : ND) : "memory");
@@ -71,89 +70,97 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---- stage A (zero rows past M) and Wk: one 16-byte chunk = 8 bf16 of one row
+    // ---- the weights are staged ONCE per CTA; the CTA then walks its tiles (persistent over blockIdx.x):
+    // one 16-byte chunk = 8 bf16 of one row
     constexpr int KC = KD / 8;
-    for (int c = tid; c < MT * KC; c += 128) {
-        const int r = c / KC, kc = c - r * KC;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (m0 + r < M) v = *reinterpret_cast<const uint4*>(A + (m0 + r) * KD + kc * 8);
-        *reinterpret_cast<uint4*>(sA + (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16) = v;
-    }
     for (int c = tid; c < ND * KC; c += 128) {
         const int n = c / KC, kc = c - n * KC;
         const uint4 v = *reinterpret_cast<const uint4*>(Wk + (size_t)n * KD + kc * 8);
         *reinterpret_cast<uint4*>(sB + (size_t)kc * LBO_B + (n >> 3) * SBO + (n & 7) * 16) = v;
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_base_s;
-
-    if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(MT, ND);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll
-        for (int k = 0; k < KD / 16; ++k) {                       // one MMA consumes K = 16 = two 16-byte chunks
-            const uint64_t ad = make_smem_desc(a0 + (uint32_t)k * 2 * LBO_A, LBO_A, SBO);
-            const uint64_t bd = make_smem_desc(b0 + (uint32_t)k * 2 * LBO_B, LBO_B, SBO);
-            umma_bf16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
-    }
-    // ---- wait for the accumulator (bounded: never hang the GPU)
-    {
-        uint32_t done = 0;
-        for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
-        }
-        if (!done && lane == 0) atomicExch(err, 1);
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue: thread = accumulator row (TMEM lane) 32*warp + lane
-    const long long m = m0 + warp * 32 + lane;
-    const bool valid = m < M;
-    long long pix = valid ? m : 0;
-    const int x = (int)(pix % Wd); pix /= Wd;
-    const int y = (int)(pix % H);
-    const long long b = pix / H;
+    const long long ntiles = (M + MT - 1) / MT;
+    uint32_t phase = 0;
     const int OW = 2 * Wd;
-#pragma unroll 1
-    for (int c0 = 0; c0 < ND; c0 += 16) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (EPI == 1) {
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(Y + m * ldy + (long long)blockIdx.y * ND + c0);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, phase ^= 1u) {
+        const long long m0 = tile * MT;
+        // ---- stage A (zero rows past M)
+        for (int c = tid; c < MT * KC; c += 128) {
+            const int r = c / KC, kc = c - r * KC;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (m0 + r < M) v = *reinterpret_cast<const uint4*>(A + (m0 + r) * KD + kc * 8);
+            *reinterpret_cast<uint4*>(sA + (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                               // also: every warp has drained the previous tile's accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem = tmem_base_s;
+
+        if (tid == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(MT, ND);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            for (int k = 0; k < KD / 16; ++k) {                       // one MMA consumes K = 16 = two 16-byte chunks
+                const uint64_t ad = make_smem_desc(a0 + (uint32_t)k * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t bd = make_smem_desc(b0 + (uint32_t)k * 2 * LBO_B, LBO_B, SBO);
+                umma_bf16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
             }
-        } else if (valid) {
-            // columns c0..c0+15 : n = tap*COUT + co (COUT is a multiple of 8, so 8-column groups stay inside one tap)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        }
+        // ---- wait for the accumulator (bounded: never hang the GPU); the barrier's phase flips once per tile
+        {
+            uint32_t done = 0;
+            for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+            }
+            if (!done) { if (lane == 0) atomicExch(err, 1); break; }
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- epilogue: thread = accumulator row (TMEM lane) 32*warp + lane
+        const long long m = m0 + warp * 32 + lane;
+        const bool valid = m < M;
+        long long pix = valid ? m : 0;
+        const int x = (int)(pix % Wd); pix /= Wd;
+        const int y = (int)(pix % H);
+        const long long b = pix / H;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ND; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (EPI == 1) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(Y + m * ldy + (long long)blockIdx.y * ND + c0);
 #pragma unroll
-            for (int g = 0; g < 16; g += 8) {
-                const int n = c0 + g, tap = n / COUT, co = n - tap * COUT;
-                const int dy = tap >> 1, dx = tap & 1;
-                __nv_bfloat16 o[8];
+                    for (int e = 0; e < 4; ++e)
+                        dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                }
+            } else if (valid) {
+                // columns c0..c0+15 : n = tap*COUT + co (COUT is a multiple of 8, so 8-column groups stay inside one tap)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16(swishf(__uint_as_float(v[g + e]) + bias[co + e]));
-                __nv_bfloat16* dst = out + ((((long long)b * (2 * H) + (2 * y + dy)) * OW + (2 * x + dx)) * COUT + co);
-                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+                for (int g = 0; g < 16; g += 8) {
+                    const int n = c0 + g, tap = n / COUT, co = n - tap * COUT;
+                    const int dy = tap >> 1, dx = tap & 1;
+                    __nv_bfloat16 o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16(swishf(__uint_as_float(v[g + e]) + bias[co + e]));
+                    __nv_bfloat16* dst = out + ((((long long)b * (2 * H) + (2 * y + dy)) * OW + (2 * x + dx)) * COUT + co);
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+                }
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // pairs with the fence after the next tile's barrier
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(ND < 32 ? 32 : ND) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(ND < 32 ? 32 : ND) : "memory");
 }
 
 template <int KD, int ND>
@@ -202,14 +209,20 @@ __global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __res
 // output row, R rows per CTA: 6 MMAs per row.  Epilogue: thread = pixel reads column 0 of each accumulator, adds the
 // bias and stores fp32 (128 B per warp and row).
 struct FinalW { float w[72]; float b; };
-constexpr int FT_R = 8;                                  // output rows per CTA
 constexpr int FT_PX = 130;                               // staged pixels per row (128 + halo)
 constexpr int FT_ROWB = FT_PX * 16;                      // bytes per staged row
-constexpr int FT_ROWS = FT_R + 3;                        // halo above / below + one zero row for the padded K-chunk
-constexpr size_t FT_SMEM = (size_t)FT_ROWS * FT_ROWB + 6 * 512;
+template <int FT_R> constexpr size_t ft_smem() { return (size_t)(FT_R + 3) * FT_ROWB + 6 * 512; }
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {     // volatile: issued where written, so a batch of them is in flight together
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
+// FT_R = output rows per CTA (16 * FT_R TMEM columns: a power of two >= 32, i.e. 2, 4, 8 or 16 rows)
+template <int FT_R>
 __global__ void __launch_bounds__(128) k_conv3x3_c8_final_tc(const __nv_bfloat16* __restrict__ in, const FinalW fw, float* __restrict__ out,
                                                              int H, int Wd, int* err) {
+    constexpr int FT_ROWS = FT_R + 3;                        // halo above / below + one zero row for the padded K-chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sA = smem_raw;
     unsigned char* sB = smem_raw + (size_t)FT_ROWS * FT_ROWB;          // 6 blocks of 16 x 16 bf16 (512 B each)
@@ -237,8 +250,9 @@ __global__ void __launch_bounds__(128) k_conv3x3_c8_final_tc(const __nv_bfloat16
         const int y = y0 - 1 + sy, x = x0 - 1 + px;
         v[q] = make_uint4(0, 0, 0, 0);
         if (c < NCH && sy < FT_R + 2 && y >= 0 && y < H && x >= 0 && x < Wd)
-            v[q] = __ldg(reinterpret_cast<const uint4*>(src + ((long long)y * Wd + x) * 8));
+            v[q] = ldg_nc_v4(src + ((long long)y * Wd + x) * 8);
     }
+    __syncthreads();            // scheduling fence for ptxas: every load above is issued before the first store below
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
         const int c = tid + q * 128;
