@@ -26,7 +26,7 @@ for mode in ("fp32", "bf16"):
                  "output_write_gbs": B * 640000 / (ms * 1e-3) / 1e9}
 sr.set_precision("fp32")
 print(json.dumps({"metric": "SR decoder inference throughput", "unit": "samples/s", "batch": B, "value": res["bf16"]["samples_per_s"],
-                  "dtype": "bf16 operands / f32 accumulate (tcgen05) for 4 ConvT layers; f32 CUDA cores for Dense, ConvT 3x3, final conv",
+                  "dtype": "bf16 operands / f32 accumulate (tcgen05) for the 5 ConvT layers and the final 3x3 conv; f32 CUDA cores for Dense",
                   "flop_per_sample": FLOP_PER_SAMPLE, "paths": res, "tc_error": sr.tc_error(),
                   "roofline": {"bound": "tensor", "achieved": res["bf16"]["tflops"], "peak": peaks.get("bf16_tflops_sustained"), "unit": "TFLOP/s",
                                "frac": res["bf16"]["tflops"] / peaks.get("bf16_tflops_sustained", 1400.0),
