@@ -244,6 +244,7 @@ int run_encoder(srcfd_sr* h, const float* x_dev, int B, float* z_dev) {
     SRCK(cudaGetLastError());
     return SRCFD_OK;
 }
+constexpr int TC_PERSIST_DEFAULT = 16;      // batch 1024: 8.37 ms with one tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM
 template <int KD, int ND>
 int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* Wbf, const float* bias, __nv_bfloat16* out,
                     int B, int H) {
@@ -251,20 +252,14 @@ int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* W
     const size_t smem = srtc::convT_tc_smem<KD, ND>();
     static bool attr_done[64] = {false};                 // per device: the attribute belongs to the (device, kernel) pair
     if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc<KD, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
-    // The kernel walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with the weights staged once per CTA.  Default: one
-    // tile per CTA.  SRCFD_TC_PERSIST=1 launches only as many CTAs as fit at once (shared memory, 512 TMEM columns per
-    // SM); measured 2.5x SLOWER at batch 1024 (20.6 vs 8.4 ms): a CTA serialises stage -> MMA -> epilogue, and without a
-    // second A buffer + accumulator the tile loop loses the overlap that CTA turnover gives for free.
-    static int per_dev[64] = {0};
-    if (!per_dev[h->dev & 63]) {
-        int occ = 0, sms = 0;
-        SRCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, srtc::k_convT2x2_tc<KD, ND>, 128, smem));
-        SRCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
-        per_dev[h->dev & 63] = std::max(1, std::min(occ, 512 / (ND < 32 ? 32 : ND))) * sms;
-    }
+    // The kernel walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with the weights staged once per CTA.
+    // SRCFD_TC_PERSIST = CTAs per SM of the persistent launch (capped by the 512 TMEM columns per SM); 0 = one tile per CTA.
+    static int sms_dev[64] = {0};
+    if (!sms_dev[h->dev & 63]) SRCK(cudaDeviceGetAttribute(&sms_dev[h->dev & 63], cudaDevAttrMultiProcessorCount, h->dev));
     const long long ntiles = (M + 127) / 128;
     const char* pe = getenv("SRCFD_TC_PERSIST");
-    const unsigned grid = (pe && atoi(pe) == 1) ? (unsigned)std::min<long long>(ntiles, per_dev[h->dev & 63]) : (unsigned)ntiles;
+    const int per_sm = std::min(pe ? atoi(pe) : TC_PERSIST_DEFAULT, 512 / (ND < 32 ? 32 : ND));
+    const unsigned grid = per_sm > 0 ? (unsigned)std::min<long long>(ntiles, (long long)per_sm * sms_dev[h->dev & 63]) : (unsigned)ntiles;
     srtc::k_convT2x2_tc<KD, ND><<<grid, 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
     h->launches += 1;
     SRCK(cudaGetLastError());
