@@ -995,6 +995,12 @@ extern "C" int srcfd_coarse_solve_batch(const srcfd_params* params, int n_cases,
     }
     uint64_t smem = 0;
     if (int rc = srcfd_coarse_smem_bytes(nx, ny, &smem)) return rc;
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return fail(SRCFD_ERR_CUDA, "no CUDA device: libsrcfd has no CPU fallback");
+        if (dev < 0 || dev >= ndev) return fail(SRCFD_ERR_ARG, "bad device ordinal");
+    }
     CK(cudaSetDevice(dev));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));

@@ -42,3 +42,27 @@ def test_no_cpu_fallback():
     from srcfd import sr
     with pytest.raises(capi.SrcfdError, match="no CUDA device"):
         sr.synthetic_decoder(0).predict([[0.0] * 50])
+
+
+def test_coarse_batch_boundary_without_a_gpu():
+    """srcfd_coarse_result layout, the shared-memory sizing (a pure host function) and the size gate of the one-CTA path."""
+    from srcfd import solver as S
+    # int64, int32 x2, double[3], int64[3], int64, double[3], double[3], int32[3] + int32 pad
+    assert C.sizeof(capi.CoarseResult) == 8 + 8 + 24 + 24 + 8 + 24 + 24 + 16
+    P = 12 * 12
+    ring = max((10 - 1 + 2 * 5 - 1) // 2 + 2, (10 - 1 + 3 * 4 - 1) // 3 + 2)
+    assert capi.coarse_smem_bytes(10, 10) == 8 * (12 * P + ring * 10 * 5)
+    assert S.fits_one_cta(10, 10) and S.fits_one_cta(30, 30) and S.fits_one_cta(1, 1)
+    assert not S.fits_one_cta(48, 40) and not S.fits_one_cta(400, 400) and not S.fits_one_cta(64, 16)
+    with pytest.raises(capi.SrcfdError):
+        capi.coarse_smem_bytes(0, 10)
+
+
+@pytest.mark.skipif(capi.device_count() > 0, reason="a CUDA device is present")
+def test_coarse_batch_has_no_cpu_fallback():
+    p = capi.Params()
+    p.nx = p.ny = 10
+    p.dx = p.dy = 0.1; p.volp = 0.01; p.dt = 1e-3; p.nu = 0.01; p.rho = 1.0
+    p.inner_max, p.inner_tol = 10, 1e-6
+    with pytest.raises(capi.SrcfdError, match="no CUDA device"):
+        capi.coarse_solve_batch([p], 5, (1e-6,) * 3)
