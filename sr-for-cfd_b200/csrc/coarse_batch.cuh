@@ -13,9 +13,10 @@
 // (nx+ny)/L consecutive sweeps -- update concurrently and every stencil value a cell reads is exactly the one the
 // sequential loop would have read.  One thread owns L consecutive cells of a row and updates one of them per step.
 // A dedicated warp adds up each finished sweep's R^2 (fixed order) one step behind the workers and raises `hit`
-// when the rms meets the tolerance (LDC.py:266-268).  Sweeps past the hit have then been started already, so an
-// inner solve runs in segments: snapshot, `limit` sweeps (the previous outer iteration's count), and only when the
-// tolerance was met before the limit: restore and replay exactly that many sweeps.
+// when the rms meets the tolerance (LDC.py:266-268; evaluated as an exactly equivalent threshold on the sum, see
+// coarse_threshold); its verdict rides on the step barrier.  Sweeps past the hit have then been started already, so
+// an inner solve runs in segments: snapshot, `limit` sweeps (the previous outer iteration's count, or 2 below it for
+// long solves), and only when the tolerance was met before the limit: restore and replay exactly that many sweeps.
 #pragma once
 #include "common.cuh"
 #include "cell_ops.cuh"
