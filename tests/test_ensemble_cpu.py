@@ -64,3 +64,19 @@ def test_two_rank_gloo_gather():
     assert [g[0] for g in got] == [c.label() for c in cases]                 # gathered in sweep order
     assert [g[1] for g in got] == [i % 2 for i in range(len(cases))]         # round-robin ownership
     assert all(g[2] == int(c.Re) and g[3] == c.Re for g, c in zip(got, cases))
+
+
+def test_run_local_hands_each_case_its_warm_field():
+    """run_local(warm_fields=...) passes case i its own initial guess (the warm stage ran up front) and nothing for
+    cases without one."""
+    seen = {}
+
+    def runner(spec, device=0, max_ctas=0, warm=None, **kw):
+        seen[spec.label()] = None if warm is None else float(warm[0, 0, 0])
+        return _fake_runner(spec, device, max_ctas)
+
+    cases = E.multibc_sweep(res_ldc=(50, 100), res_bfs=(400,))
+    warm = [np.full((3, 2, 2), float(i)) if i % 2 == 0 else None for i in range(len(cases))]
+    res = E.run_local(cases, concurrency=4, runner=runner, warm_fields=warm)
+    assert [r.label for r in res] == [c.label() for c in cases]
+    assert seen == {c.label(): (float(i) if i % 2 == 0 else None) for i, c in enumerate(cases)}
