@@ -133,6 +133,34 @@ int srcfd_k_solve_momentum(srcfd_handle *h, int k, int scheme, int32_t *sweeps, 
 /* One _implicit_solve (LDC.py:432-467 / BFS.py:622-673); residual and sweep counts via srcfd_download/srcfd_status. */
 int srcfd_k_implicit_solve(srcfd_handle *h);
 
+/* ---- slab domain decomposition of a large grid over several GPUs (BASELINE configs[3]; the reference has no such
+ * path -- it is north_star's second way of sharding).  The plane is split along i into `world` contiguous slabs; a
+ * slab is an ordinary handle created with sweep_order = SRCFD_ORDER_JACOBI for the LOCAL grid: nx = halo rows towards
+ * rank-1 (0 for rank 0) + owned rows + halo rows towards rank+1 (0 for the last rank), dx/dy those of the whole domain,
+ * host arrays (srcfd_upload/_download) hold global rows own_first-halo-1 .. own_last+halo+1.  srcfd_slab_configure tells
+ * it its place; after that the srcfd_slab_* calls below replace srcfd_step / srcfd_k_solve_* for it.  They take an ARRAY
+ * of handles -- the slabs this process drives: one per process in the one-process-per-GPU layout (peers mapped with
+ * srcfd_slab_export + srcfd_slab_attach_ipc, the 64-byte blobs carried by any host channel), or several in one process
+ * (srcfd_slab_attach_local).  Halo rows and residual sums travel as peer-memory stores from the producing kernel into
+ * the consumers' mailboxes with sequence-number flags; no library collective, no host copy.  Results are those of the
+ * single-domain JACOBI order bit for bit (fields, sweep counts), for any world size.
+ * Not decomposed: QUICK's out-of-plane reads at an INFLOW boundary (hazard H4) see the local plane, not the far slab. */
+#define SRCFD_SLAB_BLOB_BYTES 64
+#define SRCFD_SLAB_MAX_WORLD 16
+int srcfd_slab_configure(srcfd_handle *h, int world, int rank, int nx_global, int halo);
+int srcfd_slab_export(srcfd_handle *h, void *blob, int blob_bytes);
+int srcfd_slab_attach_ipc(srcfd_handle *h, int peer_rank, const void *blob);
+int srcfd_slab_attach_local(srcfd_handle *h, int peer_rank, srcfd_handle *peer);
+/* owned local rows (1-based, inclusive), exchanges done, bytes pushed to neighbours, blocks replayed after an overshoot */
+int srcfd_slab_info(srcfd_handle *h, int32_t *own_row0, int32_t *own_row1, int64_t *exchanges, int64_t *halo_bytes,
+                    int64_t *replays);
+/* refresh the halo rows of plane k from the neighbours' owned rows */
+int srcfd_slab_exchange(srcfd_handle *const *hs, int n, int k);
+int srcfd_slab_solve_pressure(srcfd_handle *const *hs, int n, int32_t *sweeps, double *last_rms);            /* LDC.py:292-314 */
+int srcfd_slab_solve_momentum(srcfd_handle *const *hs, int n, int k, int scheme, int32_t *sweeps, double *last_rms); /* LDC.py:248-290 */
+/* n_outer x (_implicit_solve + _convergence_check + copy_new_to_old), LDC.py:408-419, 432-501; srcfd_status reports. */
+int srcfd_slab_step(srcfd_handle *const *hs, int n, int64_t n_outer, const double crit[3]);
+
 /* ---- batched small-grid solves: the coarse stage of the ML-accelerated workflow ---------------------------------
  * run_coarse_simulation (PyCFD_ML_accelerated.py:696-761 / bfs_ml_accelerated.py:893-977) builds a CFDSolver on the
  * lr_dim x lr_dim mesh (10x10), which zero-initialises (_initialize_fields) and runs solve() for up to 100 000 outer

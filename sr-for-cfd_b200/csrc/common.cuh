@@ -34,6 +34,7 @@ struct BcSpec {
     double values[3][4];
     int bfs;              // left-boundary override of BFS.py:524-562
     double step_h, h, Ub;
+    int skip_lo, skip_hi; // slab decomposition: row 0 / row nx+1 of the local plane belongs to a neighbour, not to the boundary
 };
 
 // Device-resident control block.  Written only by single-thread epilogue kernels or by thread 0 of

@@ -102,7 +102,7 @@ __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, dou
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             bool fail = false;
-                            nv[q] = pressure_cell3(v[q + 1], v[q + 2], v[q], cur[idx + q * RJ + 1], cur[idx + q * RJ - 1],
+                            nv[q] = pressure_cell3z(v[q + 1], v[q + 2], v[q], cur[idx + q * RJ + 1], cur[idx + q * RJ - 1],
                                                    rh[idx + q * RJ], volp, D, R[q], fail);
                             bad = bad || fail;
                         }
@@ -126,7 +126,7 @@ __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, dou
                         const double ip = cur[idx + RJ];
                         double R;
                         bool fail = false;
-                        double nv = pressure_cell3(c, ip, im, cur[idx + 1], cur[idx - 1], rh[idx], volp, D, R, fail);
+                        double nv = pressure_cell3z(c, ip, im, cur[idx + 1], cur[idx - 1], rh[idx], volp, D, R, fail);
                         if (__builtin_expect(fail, 0)) {
                             const double2 o = pressure_cell3_ieee(c, ip, im, cur[idx + 1], cur[idx - 1], rh[idx], volp, D.dx2.b,
                                                                   D.dy2.b, D.apd.b);
@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb(JtbArgs ja) {
 // [res_r0, res_r1] only (a slab's halo rows are relaxed too, but belong to the neighbour).
 // The last CTA to finish adds the per-CTA partial sums up, in CTA order (deterministic), into sums[0..nsw).
 template <int H>
-__global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int nsw, int res_r0, int res_r1, double* __restrict__ sums,
-                                                                unsigned* __restrict__ ticket) {
+__global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, const double* __restrict__ src, double* __restrict__ dst,
+                                                                int nsw, int res_r0, int res_r1, double* __restrict__ sums,
+                                                                unsigned* __restrict__ ticket, const int* __restrict__ done) {
     const SolveArgs& a = ja.s;
     if (a.ctrl->stop) return;
+    if (done && *(const volatile int*)done) return;          // slab solves: the break test was met in an earlier block
     extern __shared__ double smem[];
     __shared__ double red[32];
     const Consts& K = a.K;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, int 
     double acc[H];
 #pragma unroll
     for (int t = 0; t < H; ++t) acc[t] = 0.0;
-    jtb_pass<H>(a, a.Var + (long long)a.k * K.plane, a.scratch, nsw, smem, acc, D, res_r0, res_r1);
+    jtb_pass<H>(a, src, dst, nsw, smem, acc, D, res_r0, res_r1);
 #pragma unroll
     for (int t = 0; t < H; ++t) {
         const double tot = block_sum(acc[t], red);

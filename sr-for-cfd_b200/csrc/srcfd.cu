@@ -18,6 +18,7 @@
 #include "inner_gs2.cuh"
 #include "inner_gs3.cuh"
 #include "jacobi_tb.cuh"
+#include "slab.cuh"
 #include "coarse_batch.cuh"
 
 using namespace srcfd;
@@ -38,6 +39,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 struct EvPair { cudaEvent_t a, b; int kind; };
+struct SlabState;               // slab_api.inl
 
 struct srcfd_handle {
     srcfd_params p;
@@ -97,7 +99,12 @@ struct srcfd_handle {
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
     int inner_cap = 0;          // capacity of the per-sweep buffers (inner_max at creation)
     int guess_bias = 0;
+    // environment knobs, read once at creation (getenv is neither cheap nor safe against a concurrent setenv)
+    int gs3_k1max = 128, gs3_skip_idle = 1, gs3_pretouch = 1;
+    bool maybe_stopped = false; // srcfd_step/solve may have left Ctrl.stop set on the device
+    SlabState* slab = nullptr;  // non-null: this handle is one slab of a decomposed grid (srcfd_slab_configure)
 };
+static void slab_release(srcfd_handle* h);
 
 // Derived constants, each with the reference's own expression (host compiled with -ffp-contract=off).
 static Consts make_consts(const srcfd_params& p) {
@@ -120,6 +127,7 @@ static BcSpec make_bc(const srcfd_params& p) {
     for (int k = 0; k < 3; ++k)
         for (int s = 0; s < 4; ++s) { b.types[k][s] = p.bc_types[k][s]; b.values[k][s] = p.bc_values[k][s]; }
     b.bfs = p.bfs_enabled; b.step_h = p.bfs_step_h; b.h = p.bfs_h; b.Ub = p.bfs_Ub;
+    b.skip_lo = b.skip_hi = 0;
     return b;
 }
 
@@ -318,6 +326,7 @@ int srcfd_destroy(srcfd_handle* h) {
     if (!h) return SRCFD_OK;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    slab_release(h);
     if (h->tm_a) cudaEventDestroy(h->tm_a);
     if (h->tm_b) cudaEventDestroy(h->tm_b);
     for (auto& e : h->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -358,6 +367,9 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     if (const char* s = getenv("SRCFD_SPIN_LIMIT")) h->spin_limit = atoi(s);
     if (const char* s = getenv("SRCFD_GUESS_BIAS")) h->guess_bias = atoi(s);
     if (const char* s = getenv("SRCFD_GS_IMPL")) h->gs_impl = atoi(s);
+    if (const char* s = getenv("SRCFD_K1MAX")) h->gs3_k1max = atoi(s);
+    if (const char* s = getenv("SRCFD_SKIP_IDLE")) h->gs3_skip_idle = atoi(s);
+    if (const char* s = getenv("SRCFD_PRETOUCH")) h->gs3_pretouch = atoi(s);
     if (int rc = plan_launches(h)) return bail(rc);
     const size_t P = (size_t)h->K.plane;
     const size_t pad = 4 * (size_t)h->K.pitch + 64;   // QUICK's flat over-reads stay inside the allocation
@@ -429,7 +441,8 @@ int srcfd_set_params(srcfd_handle* h, const srcfd_params* params) {
     if (params->inner_max > h->inner_cap) return fail(SRCFD_ERR_ARG, "inner_max cannot exceed its value at creation");
     const int keep_ctas = h->p.max_ctas;
     h->p = *params; h->p.max_ctas = keep_ctas;
-    const BcSpec nb = make_bc(*params);
+    BcSpec nb = make_bc(*params);
+    nb.skip_lo = h->bc.skip_lo; nb.skip_hi = h->bc.skip_hi;   // slab sides survive a parameter change
     if (memcmp(&nb, &h->bc, sizeof(BcSpec)) != 0) h->ghosts_fresh = false;   // new BCs: ghosts no longer known consistent
     h->K = make_consts(*params); h->bc = nb;
     return SRCFD_OK;
@@ -530,10 +543,17 @@ static int l_under_relax(srcfd_handle* h, int k, double alpha) {
     return SRCFD_OK;
 }
 static int l_correct_velocity(srcfd_handle* h) {
-    k_correct_velocity<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, h->res_partials, h->K, h->ctrl);
+    k_correct_velocity<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, h->res_partials, h->K, h->ctrl, 1, h->K.nx);
     LAUNCH_CHECK(h);
-    k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl);
+    k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl, nullptr);
     LAUNCH_CHECK(h);
+    return SRCFD_OK;
+}
+static int l_clear_stop(srcfd_handle* h) {
+    if (!h->maybe_stopped) return SRCFD_OK;
+    k_clear_stop<<<1, 1, 0, h->stream>>>(h->ctrl);
+    LAUNCH_CHECK(h);
+    h->maybe_stopped = false;
     return SRCFD_OK;
 }
 static int l_zero_residual(srcfd_handle* h) {
@@ -581,11 +601,11 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
         Gs3Args g3;
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
-        g3.k1_max = getenv("SRCFD_K1MAX") ? atoi(getenv("SRCFD_K1MAX")) : 128;
+        g3.k1_max = h->gs3_k1max;
         g3.s.prog = h->trace ? h->prog : nullptr;      // this kernel has no progress flags: non-null only asks it to count polls
         g3.ll = h->gs3_ll; g3.rhsS = h->gs3_rhsS + (size_t)WF3_PAD_LO * h->gs3_stride; g3.partials = h->partials; g3.epoch = h->gs3_epoch; g3.trace = h->trace;
-        g3.skip_idle = getenv("SRCFD_SKIP_IDLE") ? atoi(getenv("SRCFD_SKIP_IDLE")) : 1;
-        g3.pretouch = getenv("SRCFD_PRETOUCH") ? atoi(getenv("SRCFD_PRETOUCH")) : 1;
+        g3.skip_idle = h->gs3_skip_idle;
+        g3.pretouch = h->gs3_pretouch;
         void* args3[] = {&g3};
         CK(cudaLaunchCooperativeKernel(h->gs3_fn, dim3(h->gs3_grid), dim3(h->gs3_RP), args3, h->gs3_smem, h->stream));
     } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
@@ -674,7 +694,7 @@ static int ctrl_verdict(srcfd_handle* h) {
 extern "C" {
 
 int srcfd_initialize_fields(srcfd_handle* h, int zero_first) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     const size_t P = (size_t)h->K.plane;
     if (zero_first) {
         CK(cudaMemsetAsync(h->Var, 0, sizeof(double) * 3 * P, h->stream));
@@ -689,7 +709,7 @@ int srcfd_initialize_fields(srcfd_handle* h, int zero_first) {
 }
 
 int srcfd_set_fields(srcfd_handle* h, const void* fields, int is_float32) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     if (!fields) return fail(SRCFD_ERR_ARG, "null fields");
     const size_t n = 3 * (size_t)h->K.nx * h->K.ny;
     const size_t bytes = n * (is_float32 ? sizeof(float) : sizeof(double));
@@ -711,6 +731,7 @@ int srcfd_set_fields(srcfd_handle* h, const void* fields, int is_float32) {
 int srcfd_step(srcfd_handle* h, int64_t n_outer, const double crit[3]) {
     CKH(h);
     if (!crit) return fail(SRCFD_ERR_ARG, "null crit");
+    h->maybe_stopped = true;
     for (int64_t it = 0; it < n_outer; ++it) {
         TRY(l_implicit_solve(h));
         k_convergence_check<<<1, 1, 0, h->stream>>>(h->ctrl, h->hist, h->K, crit[0], crit[1], crit[2]);
@@ -741,6 +762,7 @@ int srcfd_reset_counters(srcfd_handle* h) {
     TRY(fetch_ctrl(h));
     Ctrl& c = *h->ctrl_host;
     c.stop = c.converged = c.nan_flag = c.deadlock = 0;
+    h->maybe_stopped = false;
     c.iterations = 0; c.n_hist = 0;
     for (int k = 0; k < 3; ++k) { c.total_sweeps[k] = 0; c.last_sweeps[k] = 0; }
     return push_ctrl(h);
@@ -784,35 +806,35 @@ int srcfd_solve(srcfd_handle* h, int64_t max_iterations, const double crit[3], i
 }
 
 // ---- kernel-level entry points ----------------------------------------------------------------
-int srcfd_k_copy_new_to_old(srcfd_handle* h) { CKH(h); return l_copy_new_to_old(h); }
+int srcfd_k_copy_new_to_old(srcfd_handle* h) { CKH(h); TRY(l_clear_stop(h)); return l_copy_new_to_old(h); }
 int srcfd_k_apply_bc(srcfd_handle* h, int k) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k);
 }
 int srcfd_k_apply_bc_configured(srcfd_handle* h, int k) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k, 1);
 }
 int srcfd_k_apply_bfs_inlet(srcfd_handle* h, int k) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_apply_bc(h, k, 2);
 }
-int srcfd_k_linear_interpolation(srcfd_handle* h) { CKH(h); return l_linear_interpolation(h, false); }
-int srcfd_k_update_flux(srcfd_handle* h) { CKH(h); return l_update_flux(h); }
+int srcfd_k_linear_interpolation(srcfd_handle* h) { CKH(h); TRY(l_clear_stop(h)); return l_linear_interpolation(h, false); }
+int srcfd_k_update_flux(srcfd_handle* h) { CKH(h); TRY(l_clear_stop(h)); return l_update_flux(h); }
 int srcfd_k_under_relax(srcfd_handle* h, int k, double alpha) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     if (k < 0 || k > 2) return fail(SRCFD_ERR_ARG, "k must be 0, 1 or 2");
     return l_under_relax(h, k, alpha);
 }
 int srcfd_k_correct_velocity(srcfd_handle* h, double residual_out[3]) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     TRY(l_correct_velocity(h));
     if (residual_out) return srcfd_download(h, nullptr, nullptr, nullptr, residual_out);
@@ -826,7 +848,7 @@ static int finish_inner(srcfd_handle* h, int slot, int32_t* sweeps, double* last
     return ctrl_verdict(h);
 }
 int srcfd_k_solve_pressure(srcfd_handle* h, int32_t* sweeps, double* last_rms) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     TRY(l_pressure_rhs(h));
     TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
     return finish_inner(h, 2, sweeps, last_rms);
@@ -839,7 +861,7 @@ int srcfd_jacobi_pass_max(srcfd_handle* h, int* H) {
 }
 int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1, int recompute_rhs, int commit, int slot,
                         double* sums) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     if (!h->jtb_H) return fail(SRCFD_ERR_ARG, "the temporally blocked Jacobi kernel is disabled (SRCFD_JTB=0)");
     if (nsweeps < 1 || nsweeps > h->jtb_H) return fail(SRCFD_ERR_ARG, "nsweeps must be 1..srcfd_jacobi_pass_max()");
     if (own_row0 < 1 || own_row1 > h->p.nx || own_row0 > own_row1) return fail(SRCFD_ERR_ARG, "bad row range");
@@ -860,7 +882,10 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
         h->jtb_ghosts_valid = true;
     }
     double* sums_dev = h->jtb_sums + 8 * slot;
-    void* args[] = {&ja, &nsweeps, &own_row0, &own_row1, &sums_dev, &h->jtb_ticket};
+    const double* src = h->Var + 2 * (size_t)h->K.plane;
+    double* dst = h->scratch;
+    const int* done = nullptr;
+    void* args[] = {&ja, &src, &dst, &nsweeps, &own_row0, &own_row1, &sums_dev, &h->jtb_ticket, &done};
     CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
     h->launches += 1;
     if (commit) {
@@ -889,7 +914,7 @@ int srcfd_jacobi_sums_ptr(srcfd_handle* h, uint64_t* ptr) {
     return SRCFD_OK;
 }
 int srcfd_k_jacobi_commit(srcfd_handle* h) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     SolveArgs a;
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
@@ -901,14 +926,14 @@ int srcfd_k_jacobi_commit(srcfd_handle* h) {
     return SRCFD_OK;
 }
 int srcfd_k_solve_momentum(srcfd_handle* h, int k, int scheme, int32_t* sweeps, double* last_rms) {
-    CKH(h);
+    CKH(h); TRY(l_clear_stop(h));
     h->ghosts_fresh = false;
     if (k < 0 || k > 1) return fail(SRCFD_ERR_ARG, "momentum is solved for k = 0 (u) or 1 (v)");
     if (scheme != SRCFD_SCHEME_UPWIND && scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
     TRY(l_inner_solve(h, scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND, k, k));
     return finish_inner(h, k, sweeps, last_rms);
 }
-int srcfd_k_implicit_solve(srcfd_handle* h) { CKH(h); return l_implicit_solve(h); }
+int srcfd_k_implicit_solve(srcfd_handle* h) { CKH(h); TRY(l_clear_stop(h)); return l_implicit_solve(h); }
 
 int srcfd_timer_start(srcfd_handle* h) {
     CKH(h);
@@ -928,6 +953,8 @@ int srcfd_timer_stop(srcfd_handle* h, double* ms) {
 }
 int srcfd_debug_read(srcfd_handle* h, double* out, int64_t n) {   // debug builds: raw doubles stored behind the scratch plane
     CKH(h);
+    const int64_t slack = 4 * (int64_t)h->K.pitch + 8192;       // what srcfd_create allocated behind the plane (pad + 8192 - 64)
+    if (!out || n < 0 || n > slack) return fail(SRCFD_ERR_ARG, "srcfd_debug_read: n exceeds the slack behind the scratch plane");
     CK(cudaMemcpy(out, h->scratch + h->K.plane + 64, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return SRCFD_OK;
 }
@@ -1069,3 +1096,5 @@ extern "C" int srcfd_coarse_solve_batch(const srcfd_params* params, int n_cases,
     if (st) cudaStreamDestroy(st);
     return rc;
 }
+
+#include "slab_api.inl"

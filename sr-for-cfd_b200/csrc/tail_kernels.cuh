@@ -30,13 +30,13 @@ __global__ void k_copy_new_to_old(const double* __restrict__ Var, double* __rest
 // mode: 0 = both (the wrapper), 1 = apply_bc_configured only, 2 = _apply_bfs_inlet only.
 __global__ void k_apply_bc(double* __restrict__ Var, int k, Consts K, BcSpec bc, int mode, const Ctrl* ctrl) {
     if (ctrl->stop) return;
-    const bool generic = (mode != 2), inlet = (mode != 1) && bc.bfs && (k == 0 || k == 1);
+    const bool generic = (mode != 2), inlet = (mode != 1) && bc.bfs && (k == 0 || k == 1) && !bc.skip_lo;
     const int t = blockIdx.x * blockDim.x + threadIdx.x + 1;
     double* V = Var + (long long)k * K.plane;
     if (mode == 4) {
         // only the side effect of the k = 0 inlet pass on the v ghost column (BFS.py:562), so that a paired u/v solve
         // sees the column the reference's v solve would see
-        if (bc.bfs && t <= K.ny && (t - 0.5) * K.dy >= bc.step_h) {
+        if (bc.bfs && !bc.skip_lo && t <= K.ny && (t - 0.5) * K.dy >= bc.step_h) {
             double* Vv = Var + K.plane;
             Vv[t] = -Vv[K.pitch + t];
         }
@@ -44,9 +44,11 @@ __global__ void k_apply_bc(double* __restrict__ Var, int k, Consts K, BcSpec bc,
     }
     if (t <= K.ny) {
         const int j = t;
-        if (generic) {
+        if (generic && !bc.skip_lo) {
             if (bc.types[k][0] == 0) V[j] = 2 * bc.values[k][0] - V[K.pitch + j];
             else                     V[j] = V[K.pitch + j];
+        }
+        if (generic && !bc.skip_hi) {
             const long long r = (long long)(K.nx + 1) * K.pitch + j, q = (long long)K.nx * K.pitch + j;
             if (bc.types[k][1] == 0) V[r] = 2 * bc.values[k][1] - V[q];
             else                     V[r] = V[q];
@@ -127,7 +129,7 @@ __global__ void k_under_relax(double* __restrict__ Var, const double* __restrict
 // LDC.py:316-328 correct_velocity.  Residual sums: per-block partials in a fixed order, finished by
 // k_residual_finish -- deterministic, but not the reference's sequential order (differs in the last bits).
 __global__ void k_correct_velocity(double* __restrict__ Var, const double* __restrict__ VarOld,
-                                   double* __restrict__ partials, Consts K, const Ctrl* ctrl) {
+                                   double* __restrict__ partials, Consts K, const Ctrl* ctrl, int res_r0, int res_r1) {
     if (ctrl->stop) return;
     __shared__ double scratch[3][32];
     int i, j; long long c;
@@ -139,7 +141,7 @@ __global__ void k_correct_velocity(double* __restrict__ Var, const double* __res
         const double v = V[c] - K.dt_rho * (P[c + 1] - P[c - 1]) / K.two_dy;
         U[c] = u; V[c] = v;
         const double du = u - UO[c], dv = v - VO[c], dp = P[c] - PO[c];
-        du2 = du * du; dv2 = dv * dv; dp2 = dp * dp;
+        if (i >= res_r0 && i <= res_r1) { du2 = du * du; dv2 = dv * dv; dp2 = dp * dp; }   // a slab counts its own rows only
     }
     const double su = block_sum(du2, scratch[0]);
     const double sv = block_sum(dv2, scratch[1]);
@@ -150,17 +152,22 @@ __global__ void k_correct_velocity(double* __restrict__ Var, const double* __res
 }
 
 // residual[k] += sum of partials (fixed order: strided lanes, then block_sum).  One block.
-__global__ void k_residual_finish(const double* __restrict__ partials, int nblocks, Ctrl* ctrl) {
+// out != null: the three sums go there instead (a slab hands them to the exchange that adds the ranks up).
+__global__ void k_residual_finish(const double* __restrict__ partials, int nblocks, Ctrl* ctrl, double* __restrict__ out) {
     if (ctrl->stop) return;
     __shared__ double scratch[32];
     for (int k = 0; k < 3; ++k) {
         double s = 0.0;
         for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[3 * b + k];
         const double tot = block_sum(s, scratch);
-        if (threadIdx.x == 0) ctrl->residual[k] += tot;
+        if (threadIdx.x == 0) { if (out) out[k] = tot; else ctrl->residual[k] += tot; }
         __syncthreads();
     }
 }
+
+// A solve()/step() that ended converged or with NaN leaves stop = 1 so that the launches queued behind it are no-ops;
+// the next kernel-level or composed call starts from a clean verdict (the reference's methods always run).
+__global__ void k_clear_stop(Ctrl* ctrl) { ctrl->stop = 0; ctrl->converged = 0; ctrl->nan_flag = 0; }
 
 __global__ void k_zero_residual(Ctrl* ctrl) {
     if (ctrl->stop) return;

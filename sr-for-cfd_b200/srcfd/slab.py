@@ -1,6 +1,14 @@
-"""Slab domain decomposition of the pressure relaxation across GPUs (BASELINE configs[3]: a large grid split along i).
+"""Slab domain decomposition of the fine-grid iteration across GPUs (BASELINE configs[3]: a large grid split along i).
 
-Scope: the JACOBI-order pressure solve (the order BASELINE's north star names for the decomposed grid), i.e.
+Product path: `GpuSlab` + the group functions at the bottom (solve_pressure / solve_momentum / step) bind libsrcfd's
+srcfd_slab_* entry points: the whole JACOBI-order outer iteration (PyCFD_ML_accelerated.py:432-501) decomposed, halo
+rows and residual sums moved by the kernels themselves through peer-mapped memory (csrc/slab.cuh), the block loop and
+the break rule inside the library.  torch.distributed is used ONCE, at set-up, to hand the 64-byte cudaIpc blobs round.
+
+The two `slab_jacobi_solve*` functions below are the executable model of that block protocol (back-end agnostic: pass /
+commit / exchange / all-reduce are callables); the CPU tests run them under gloo with the oracle's arithmetic.
+
+Model scope: the JACOBI-order pressure solve (the order BASELINE's north star names for the decomposed grid), i.e.
 solve_pressure (PyCFD_ML_accelerated.py:292-314) with every cell of a sweep computed from the previous iterate.  One
 process per GPU; rank r owns a contiguous block of interior rows.  The temporally blocked kernel advances H sweeps per
 pass; a slab carries M*H halo rows on each side that has a neighbour and exchanges them once per M passes (M*H sweeps),
@@ -139,136 +147,137 @@ def slab_jacobi_solve_blocks(part: SlabPartition, ncells_global: int, tol: float
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# GPU back-end: one libsrcfd handle per rank on the local grid, torch.distributed for halos and the all-reduce
+# GPU path: libsrcfd's srcfd_slab_* entry points (csrc/slab.cuh, csrc/slab_api.inl)
 # ---------------------------------------------------------------------------------------------------------------------
-class _DevRows:
-    """H contiguous rows of the library's pressure plane as a CUDA array (no copy): torch.as_tensor(obj) aliases them."""
-
-    def __init__(self, ptr: int, rows: int, pitch: int):
-        self.__cuda_array_interface__ = {"shape": (rows, pitch), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
-                                         "strides": None}
+DEFAULT_HALO = 16
 
 
 class GpuSlab:
-    """Pressure plane of one slab on one GPU.  p_global / Ff_global are the full-domain arrays (every rank builds or
-    loads the same ones; only the local rows are uploaded)."""
+    """One slab (rank) of a decomposed flow case on one GPU.
 
-    def __init__(self, nx: int, ny: int, dx: float, dy: float, dt: float, rho: float, Var_global: np.ndarray,
-                 Ff_global: np.ndarray, world: int, rank: int, device: int = 0, halo: Optional[int] = None,
-                 passes_per_exchange: int = 8):
+    params: srcfd Params of the WHOLE case (nx = global rows; dx, dy, BCs, ... as for an undivided handle;
+    params.device = the CUDA device of THIS rank).  The local handle owns global rows part.global_rows()."""
+
+    def __init__(self, params, world: int, rank: int, halo: int = DEFAULT_HALO):
+        import copy
+        import ctypes as C
         from . import _capi as capi
         self.capi = capi
-        # the halo depth is the number of sweeps per pass of the kernel for a grid of the LOCAL size
-        H_guess = 4 if (nx // world) * ny >= (1 << 20) else 8
-        probe = halo if halo is not None else H_guess * max(1, passes_per_exchange)
-        probe = max(1, min(probe, nx // world))             # a slab cannot be thinner than its halo
-        self.part = SlabPartition(nx, world, rank, probe if world > 1 else 0)
-        p = capi.Params()
-        p.nx, p.ny = self.part.nx_local, ny
-        p.dx, p.dy, p.volp, p.dt, p.nu, p.rho = dx, dy, dx * dy, dt, 1.0, rho
-        p.scheme, p.inner_tol, p.inner_max, p.sweep_order, p.device = 0, 0.0, 1000, capi.ORDER_JACOBI, device
-        for k in range(3):
-            for s in range(4):
-                p.bc_types[k][s] = 1 if k == 2 else 0
-        self.h = capi.Handle(p)
-        self.H = self.h.jacobi_pass_max()
-        self.nsw_max = min(self.H, self.part.halo) if world > 1 else self.H      # sweeps per kernel pass
-        self.ny, self.pitch = ny, ny + 2
-        self.ncells_global = nx * ny
+        self.nx_global, self.ny = params.nx, params.ny
+        self.part = SlabPartition(params.nx, world, rank, halo if world > 1 else 0)
+        local = type(params).from_buffer_copy(bytes(params))
+        local.nx = self.part.nx_local
+        local.sweep_order = capi.ORDER_JACOBI
+        self.h = capi.Handle(local)
+        capi.check(capi.lib().srcfd_slab_configure(self.h._h, C.c_int(world), C.c_int(rank), C.c_int(params.nx), C.c_int(halo)))
+
+    # ---- state
+    def _rows(self, a):
         g0, g1 = self.part.global_rows()
-        self.h.upload(Var=np.ascontiguousarray(Var_global[:, g0:g1 + 1]), Ff=np.ascontiguousarray(Ff_global[:, g0:g1 + 1]))
-        self._rhs_done = False
-        ptrs = self.h.device_ptrs()
-        self.p_ptr = ptrs[0] + 2 * (self.part.nx_local + 2) * self.pitch * 8       # plane k = 2
-        self._sums = None
-        self._ext = None
+        return np.ascontiguousarray(a[:, g0:g1 + 1])
 
-    # rows as torch tensors aliasing the library's memory
-    def _rows(self, first_row: int, nrows: int):
-        import torch
-        return torch.as_tensor(_DevRows(self.p_ptr + first_row * self.pitch * 8, nrows, self.pitch), device=f"cuda:{self.h.params.device}")
+    def upload_global(self, Var=None, VarOld=None, Ff=None):
+        """Upload this slab's rows of full-domain (3|4, nx+2, ny+2) arrays."""
+        self.h.upload(Var=None if Var is None else self._rows(Var), VarOld=None if VarOld is None else self._rows(VarOld),
+                      Ff=None if Ff is None else self._rows(Ff))
 
-    def run_pass(self, nsw: int, commit_now, slot: Optional[int] = None):
-        """Enqueue one pass; the per-sweep sums stay on the device (slot `slot` of jacobi_sums_ptr).  Two calling
-        conventions: run_pass(nsw, commit_now) for slab_jacobi_solve, run_pass(nsw, slot) (always commits) for the
-        block driver."""
-        if slot is None and not isinstance(commit_now, bool):
-            slot, commit_now = int(commit_now), True
-        self.h.k_jacobi_pass_device(nsw, self.part.local_own0, self.part.local_own1, recompute_rhs=not self._rhs_done,
-                                    commit=bool(commit_now), slot=slot or 0)
-        self._rhs_done = True
-        return np.zeros(nsw)                                 # placeholder: the values live at jacobi_sums_ptr
+    def download_local(self):
+        nxl = self.part.nx_local
+        Var = np.zeros((3, nxl + 2, self.ny + 2)); VarOld = np.zeros_like(Var); Ff = np.zeros((4, nxl + 2, self.ny + 2))
+        self.h.download(Var=Var, VarOld=VarOld, Ff=Ff)
+        return Var, VarOld, Ff
 
-    def snapshot(self):
-        self.h.k_jacobi_snapshot(False)
-
-    def restore(self):
-        self.h.k_jacobi_snapshot(True)
-
-    def _sums_tensor(self):
-        import torch
-        if self._sums is None:
-            self._sums = torch.as_tensor(_DevRows(self.h.jacobi_sums_ptr(), 16, 8), device=f"cuda:{self.h.params.device}")
-        return self._sums
-
-    def reduce(self, nslots: int) -> np.ndarray:
-        """(nslots, 8) per-sweep sums of the last block, summed over the ranks (one collective, one synchronisation)."""
-        import torch.distributed as dist
-        t = self._sums_tensor()
-        with self._stream():
-            if self.part.world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            return t[:nslots].cpu().numpy()                  # the one synchronisation of a block
-
-    def read_sums(self, n: int) -> np.ndarray:
-        """Per-sweep sums of the last pass (this slab's owned rows), copied to the host."""
-        self.h.synchronize()
-        return self._sums_tensor()[0, :n].cpu().numpy()
-
-    def commit(self):
-        self.h.k_jacobi_commit()
-
-    def _stream(self):
-        """The library's own stream as a torch stream: collectives issued under it are ordered with the kernels, so the
-        block loop needs no host synchronisation besides reading the reduced sums."""
-        import torch
-        if self._ext is None:
-            self._ext = torch.cuda.ExternalStream(self.h.stream(), device=f"cuda:{self.h.params.device}")
-        return torch.cuda.stream(self._ext)
-
-    def exchange(self):
-        """Owned edge rows -> neighbours' halo rows (NCCL point-to-point, both directions in one batch)."""
-        import torch.distributed as dist
-        P = self.part
-        if P.world == 1:
-            return
-        ops = []
-        if P.lo:        # neighbour above: send my first H owned rows, receive its last H owned rows into my upper halo
-            ops += [dist.P2POp(dist.isend, self._rows(P.local_own0, P.halo), P.rank - 1),
-                    dist.P2POp(dist.irecv, self._rows(1, P.halo), P.rank - 1)]
-        if P.hi:
-            ops += [dist.P2POp(dist.isend, self._rows(P.local_own1 - P.halo + 1, P.halo), P.rank + 1),
-                    dist.P2POp(dist.irecv, self._rows(P.local_own1 + 1, P.halo), P.rank + 1)]
-        with self._stream():
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()                                     # stream-level wait: the next pass is ordered after the receive
-
-    def allreduce_sum(self, v: np.ndarray) -> np.ndarray:
-        import torch, torch.distributed as dist
-        t = self._sums_tensor()[0]
-        with self._stream():
-            if self.part.world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            return t[: len(v)].cpu().numpy()
-
-    def solve(self, tol: float = 1e-6, max_iter: int = 1000) -> Tuple[int, float]:
-        part = self.part if self.part.world > 1 else SlabPartition(self.part.nx, 1, 0, self.H)
-        M = max(1, min(16, part.halo // self.nsw_max)) if self.part.world > 1 else 8
-        return slab_jacobi_solve_blocks(part, self.ncells_global, tol, max_iter, self, self.nsw_max, M)
+    def owned(self):
+        """(Var, VarOld, Ff) restricted to the owned rows: shapes (3|3|4, n_own, ny+2)."""
+        a, b = self.part.local_own0, self.part.local_own1 + 1
+        return tuple(x[:, a:b].copy() for x in self.download_local())
 
     def owned_rows(self) -> np.ndarray:
         """(n_own, ny+2) owned rows of the pressure plane."""
-        nxl = self.part.nx_local
-        Var = np.zeros((3, nxl + 2, self.ny + 2))
-        self.h.download(Var=Var)
-        return Var[2, self.part.local_own0:self.part.local_own1 + 1].copy()
+        return self.owned()[0][2]
+
+    def info(self) -> dict:
+        import ctypes as C
+        r0, r1 = C.c_int32(0), C.c_int32(0)
+        ex, hb, rp = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self.capi.check(self.capi.lib().srcfd_slab_info(self.h._h, C.byref(r0), C.byref(r1), C.byref(ex), C.byref(hb), C.byref(rp)))
+        return dict(own_row0=r0.value, own_row1=r1.value, exchanges=ex.value, halo_bytes=hb.value, replays=rp.value)
+
+    def export_blob(self) -> bytes:
+        import ctypes as C
+        buf = (C.c_ubyte * 64)()
+        self.capi.check(self.capi.lib().srcfd_slab_export(self.h._h, buf, C.c_int(64)))
+        return bytes(buf)
+
+    def attach_blob(self, peer_rank: int, blob: bytes):
+        import ctypes as C
+        buf = (C.c_ubyte * 64).from_buffer_copy(blob)
+        self.capi.check(self.capi.lib().srcfd_slab_attach_ipc(self.h._h, C.c_int(peer_rank), buf))
+
+    def close(self):
+        self.h.close()
+
+
+def attach_local(slabs):
+    """Several slabs driven by ONE process: map each one's mailbox into the others (same device: plain pointers)."""
+    import ctypes as C
+    from . import _capi as capi
+    for a in slabs:
+        for b in slabs:
+            if a is not b:
+                capi.check(capi.lib().srcfd_slab_attach_local(a.h._h, C.c_int(b.part.rank), b.h._h))
+
+
+def attach_distributed(slab: GpuSlab, group=None):
+    """One process per GPU: hand the cudaIpc blobs round with torch.distributed (set-up only; any backend) and map the
+    peers' mailboxes.  After this no torch / NCCL call is involved in the data path."""
+    import torch.distributed as dist
+    world = slab.part.world
+    if world == 1:
+        return
+    blobs = [None] * world
+    dist.all_gather_object(blobs, slab.export_blob(), group=group)
+    for q in range(world):
+        if q != slab.part.rank:
+            slab.attach_blob(q, blobs[q])
+    dist.barrier(group=group)
+
+
+def _harr(slabs):
+    import ctypes as C
+    return (C.c_void_p * len(slabs))(*[s.h._h for s in slabs]), C.c_int(len(slabs))
+
+
+def exchange(slabs, k: int):
+    import ctypes as C
+    from . import _capi as capi
+    arr, n = _harr(slabs)
+    capi.check(capi.lib().srcfd_slab_exchange(arr, n, C.c_int(k)))
+
+
+def solve_pressure(slabs) -> Tuple[int, float]:
+    """solve_pressure (PyCFD_ML_accelerated.py:292-314), JACOBI order, over the slabs this process drives."""
+    import ctypes as C
+    from . import _capi as capi
+    arr, n = _harr(slabs)
+    sw, rms = C.c_int32(0), C.c_double(0.0)
+    capi.check(capi.lib().srcfd_slab_solve_pressure(arr, n, C.byref(sw), C.byref(rms)))
+    return sw.value, rms.value
+
+
+def solve_momentum(slabs, k: int, scheme: int) -> Tuple[int, float]:
+    import ctypes as C
+    from . import _capi as capi
+    arr, n = _harr(slabs)
+    sw, rms = C.c_int32(0), C.c_double(0.0)
+    capi.check(capi.lib().srcfd_slab_solve_momentum(arr, n, C.c_int(k), C.c_int(scheme), C.byref(sw), C.byref(rms)))
+    return sw.value, rms.value
+
+
+def step(slabs, n_outer: int, crit=(1e-6, 1e-6, 1e-6)):
+    """n_outer x (_implicit_solve + _convergence_check), PyCFD_ML_accelerated.py:408-419."""
+    import ctypes as C
+    from . import _capi as capi
+    arr, n = _harr(slabs)
+    c = (C.c_double * 3)(*[float(x) for x in crit])
+    capi.check(capi.lib().srcfd_slab_step(arr, n, C.c_int64(int(n_outer)), c))

@@ -435,3 +435,26 @@ def test_long_run_with_drifting_sweep_counts_kernel_path(nx, ny, Re, its):
     assert list(s.total_sweeps) == o.total_sweeps.tolist()
     assert np.array_equal(s.Var, o.Var) and np.array_equal(s.VarOld, o.VarOld) and np.array_equal(s.Ff, o.Ff)
     assert 3 * its < o.total_sweeps[2] < 1000 * its          # neither at the cap throughout nor trivially short
+
+
+def test_methods_still_run_after_a_converged_solve():
+    """A converged (or NaN) solve leaves the device-side stop flag set so that the iterations queued behind it are no-ops;
+    the reference's methods always run, so the next _apply_bc_wrapper / _implicit_solve on the same solver must too."""
+    from srcfd import ldc
+    st = ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=400,
+                            convergence_criteria={'u': 1.6, 'v': 1.0, 'p': 26.0, 'continuity': 26.0})
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=48, ny=40), ldc.FluidProperties(Re=100.0), st, ldc.BoundaryConditions())
+    s.resident_solve = False                               # the whole-GPU kernels (the handle with the stop flag)
+    n, _ = s.solve("x", verbose=False, save=False)
+    o = O.OracleSolver(O.Case(nx=48, ny=40, Re=100.0, dt=1e-3, scheme="QUICK"))
+    m, _, _ = o.solve(400, (1.6, 1.0, 26.0))
+    assert n == m and 1 < n < 400 and np.array_equal(s.Var, o.Var)
+    s.bc.u_boundaries['top'] = ldc.BoundaryCondition('dirichlet', 2.0)       # change a BC, as the reference's callers may
+    for k in range(3):
+        o.p.bc_values[0][2] = 2.0
+        s._apply_bc_wrapper(k); o.apply_bc(k)
+    assert np.array_equal(s.Var, o.Var) and s.Var[0, 5, -1] != 0.0
+    before = s.Var.copy()
+    s._implicit_solve(); o.implicit_solve()
+    assert not np.array_equal(s.Var, before)
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
