@@ -175,7 +175,8 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         for (int t = 0; t < nsw; ++t) {
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
-            const dim3 grid((h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS, h->K.nx);
+            const int gx = (h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS;
+            const dim3 grid(gx, std::max(1, std::min(h->K.nx, (h->num_sms * 8 + gx - 1) / gx)));
             if (op == OP_UPWIND)
                 k_slab_sweep<OP_UPWIND><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done);
             else

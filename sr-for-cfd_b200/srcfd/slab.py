@@ -194,7 +194,9 @@ class GpuSlab:
 
     def owned_rows(self) -> np.ndarray:
         """(n_own, ny+2) owned rows of the pressure plane."""
-        return self.owned()[0][2]
+        Var = np.zeros((3, self.part.nx_local + 2, self.ny + 2))
+        self.h.download(Var=Var)
+        return Var[2, self.part.local_own0:self.part.local_own1 + 1].copy()
 
     def info(self) -> dict:
         import ctypes as C
