@@ -107,30 +107,18 @@ def device_count() -> int:
     return n.value if rc == OK else 0
 
 
-class _PinnedBuffer:
-    """Page-locked host block exposed through the buffer protocol; freed when the last numpy view goes away."""
-
-    def __init__(self, nbytes: int):
-        self.n = int(nbytes)
-        self.p = C.c_void_p()
-        check(lib().srcfd_host_alloc(C.c_uint64(self.n), C.byref(self.p)))
-
-    def __buffer__(self, flags):
-        return memoryview((C.c_char * self.n).from_address(self.p.value)).cast("B")
-
-    def __del__(self):
-        try:
-            if self.p:
-                lib().srcfd_host_free(self.p)
-                self.p = C.c_void_p()
-        except Exception:
-            pass
-
-
 def pinned_zeros(shape, dtype=np.float64) -> np.ndarray:
-    """np.zeros in page-locked memory (srcfd_host_alloc): same array semantics, full-rate upload/download."""
-    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    a = np.frombuffer(_PinnedBuffer(max(n, 1)), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    """np.zeros in page-locked memory (srcfd_host_alloc): same array semantics, full-rate upload/download.
+    The block is wrapped through ctypes (no Python-version-specific buffer protocol) and freed by a finalizer tied to
+    the ctypes object, which every numpy view keeps alive through its .base chain."""
+    import weakref
+    count = int(np.prod(shape))
+    n = max(count * np.dtype(dtype).itemsize, 1)
+    p = C.c_void_p()
+    check(lib().srcfd_host_alloc(C.c_uint64(n), C.byref(p)))
+    raw = (C.c_char * n).from_address(p.value)
+    weakref.finalize(raw, lib().srcfd_host_free, C.c_void_p(p.value))
+    a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
     a[...] = 0
     return a
 

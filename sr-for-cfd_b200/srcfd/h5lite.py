@@ -350,9 +350,10 @@ class _Writer:
 
     def object_header(self, msgs) -> int:
         body = b""
-        for mtype, data in msgs:
+        for m in msgs:
+            mtype, data, flags = (m + (0,))[:3]
             data = self._pad8(data)
-            body += struct.pack("<HHBBBB", mtype, len(data), 0, 0, 0, 0) + data
+            body += struct.pack("<HHBBBB", mtype, len(data), flags, 0, 0, 0) + data
         hdr = struct.pack("<BBHII", 1, 0, len(msgs), 1, len(body)) + b"\0" * 4
         return self.alloc(hdr + body)
 
@@ -361,7 +362,10 @@ class _Writer:
         if arr.dtype.kind == "f" and arr.dtype.byteorder == ">":
             arr = arr.astype(arr.dtype.newbyteorder("<"))
         data_off = self.alloc(arr.tobytes()) if arr.size else _UNDEF
-        msgs = [(0x0001, self.space_msg(arr.shape)), (0x0003, self.dtype_msg(arr.dtype)),
+        # the messages h5py's create_dataset emits, in its order: dataspace, datatype (constant), fill value v2
+        # (allocate late, write if set, defined, no value; constant), contiguous layout v3
+        msgs = [(0x0001, self.space_msg(arr.shape)), (0x0003, self.dtype_msg(arr.dtype), 1),
+                (0x0005, bytes([2, 2, 2, 1, 0, 0, 0, 0]), 1),
                 (0x0008, struct.pack("<BBQQ", 3, 1, data_off, arr.nbytes))]
         msgs += [(0x000C, self.attr_msg(k, v)) for k, v in attrs.items()]
         return self.object_header(msgs)

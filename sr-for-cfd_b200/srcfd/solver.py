@@ -348,8 +348,10 @@ class CFDSolver:
         from . import h5lite
         root = h5lite.read_h5(filename) if os.path.exists(filename) else h5lite.Group()
         grp = h5lite.Group()
-        grp.attrs = {"case_name": self.case_name, "reynolds_number": self.fluid.Re, "nx": self.mesh.nx,
-                     "ny": self.mesh.ny, "total_points": self.mesh.nx * self.mesh.ny}
+        grp.attrs = {"case_name": self.case_name, "reynolds_number": self.fluid.Re, "nx": self.mesh.nx, "ny": self.mesh.ny}
+        if getattr(self, 'case_type', None) == 'BFS':        # BFS.py:734-741 adds the domain and the step
+            grp.attrs.update({"lx": self.mesh.lx, "ly": self.mesh.ly, "step_height": self.step_height})
+        grp.attrs["total_points"] = self.mesh.nx * self.mesh.ny
         x = np.linspace(0, self.mesh.lx, self.mesh.nx)
         y = np.linspace(0, self.mesh.ly, self.mesh.ny)
         X, Y = np.meshgrid(x, y)

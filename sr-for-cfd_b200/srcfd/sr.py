@@ -78,16 +78,42 @@ def glorot_decoder_weights(seed: int = 0) -> dict:
     return w
 
 
+def resolve_layers(weights: dict, layers, shapes) -> dict:
+    """Map the layers of a weight file onto the canonical layer list BY KERNEL SHAPE, not by name.
+
+    Keras numbers auto-named layers per session: a decoder built after the encoder in the same notebook
+    (sr-ae-conv.ipynb) gets 'dense_1', 'conv2d_transpose_5', ...; the kernel shapes of both networks are pairwise
+    distinct, so each canonical layer is the one unused layer of the file whose kernel has its shape (an exact name
+    match wins when several qualify).  Returns {canonical/kernel|bias: array}; ValueError names what is missing."""
+    have = [k[:-len("/kernel")] for k in weights if k.endswith("/kernel")]
+    used, out = set(), {}
+    for name in layers:
+        want = tuple(shapes[name])
+        cands = [l for l in have if l not in used and tuple(weights[f"{l}/kernel"].shape) == want]
+        if name in cands:
+            pick = name
+        elif len(cands) >= 1:
+            pick = cands[0]
+        else:
+            got = {l: tuple(weights[f"{l}/kernel"].shape) for l in have}
+            if name in got:
+                raise ValueError(f"{name}/kernel has shape {got[name]}, expected {want}")
+            raise ValueError(f"no layer with a {want} kernel for '{name}' in the weight file (layers: {got})")
+        if f"{pick}/bias" not in weights:
+            raise ValueError(f"layer '{pick}' has a kernel but no bias")
+        used.add(pick)
+        out[f"{name}/kernel"], out[f"{name}/bias"] = weights[f"{pick}/kernel"], weights[f"{pick}/bias"]
+    return out
+
+
 class _Model:
     kind = ""
 
     def __init__(self, weights: dict, device=None):
+        layers, shapes = (ENCODER_LAYERS, ENCODER_SHAPES) if self.kind == "enc" else (DECODER_LAYERS, DECODER_SHAPES)
+        weights = resolve_layers(weights, layers, shapes)
         self.weights = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
         self.device = default_device if device is None else device
-        layers, shapes = (ENCODER_LAYERS, ENCODER_SHAPES) if self.kind == "enc" else (DECODER_LAYERS, DECODER_SHAPES)
-        for n in layers:
-            if self.weights[f"{n}/kernel"].shape != shapes[n]:
-                raise ValueError(f"{n}/kernel has shape {self.weights[f'{n}/kernel'].shape}, expected {shapes[n]}")
         self._layers = layers
 
     def _bind(self):
@@ -134,9 +160,10 @@ def load_model(path_or_model, compile=False):
     if not os.path.exists(path_or_model):
         raise OSError(f"No file or directory found at {path_or_model}")
     w = read_keras_weights(path_or_model)
-    if "latent_vector/kernel" in w:
+    kshapes = {tuple(v.shape) for k, v in w.items() if k.endswith("/kernel")}
+    if ENCODER_SHAPES["latent_vector"] in kshapes and ENCODER_SHAPES["conv2d"] in kshapes:
         return Encoder(w)
-    if "output_image_400/kernel" in w:
+    if DECODER_SHAPES["output_image_400"] in kshapes and DECODER_SHAPES["dense"] in kshapes:
         return Decoder(w)
     raise ValueError(f"{path_or_model}: not an encoder_10 / decoder_400 weight file")
 

@@ -147,7 +147,11 @@ def data_files():
                     os.path.join(HERE, "encoder10_multiBC.h5"))
     shutil.copyfile(os.path.join(REF, "standardization_stats_10to400_swish_trained_upto_700_multiBC.txt"),
                     os.path.join(HERE, "stats_10to400_multiBC.txt"))
-    print("encoder + stats copied")
+    # output-format fixtures: one committed coarse result file (h5py layout) and the centerline text file
+    src = sorted(glob.glob(os.path.join(REF, "outputs", "*", "bfs_coarse_Re400_10x10_100000_coarse_iterations.h5")))[0]
+    shutil.copyfile(src, os.path.join(HERE, "ref_bfs_coarse_Re400_10x10.h5"))
+    shutil.copyfile(os.path.join(REF, "outputs", "bfs_Re400_centerline.dat"), os.path.join(HERE, "ref_bfs_Re400_centerline.dat"))
+    print("encoder + stats + output-format fixtures copied")
 
 
 if __name__ == "__main__":
