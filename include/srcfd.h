@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SRCFD_ABI_VERSION 1
+#define SRCFD_ABI_VERSION 2   /* 2: srcfd_slab_* entry points, srcfd_params.sor_omega (carved out of reserved[]; layout and size unchanged) */
 
 enum { SRCFD_SCHEME_UPWIND = 0, SRCFD_SCHEME_QUICK = 1 };           /* SolverSettings.scheme, LDC.py:95 */
 enum {
@@ -54,7 +54,9 @@ typedef struct srcfd_params {
     int32_t sweep_order;         /* SRCFD_ORDER_*                                                    */
     int32_t device;              /* CUDA device ordinal                                              */
     int32_t max_ctas;            /* 0 = whole GPU; >0 caps the persistent grids (ensemble members)   */
-    int32_t reserved[8];
+    double  sor_omega;           /* over-relaxation factor of the RED_BLACK pressure sweep (red-black SOR, north_star):  */
+                                 /*   p += omega * R/ap instead of p += R/ap; 0 or 1 = plain sweep.  Other orders ignore it */
+    int32_t reserved[6];
 } srcfd_params;
 
 typedef struct srcfd_handle srcfd_handle;

@@ -291,6 +291,11 @@ class OracleSolver:
         return int(n), last, hist[: nh.value]
 
 
+def set_sor_omega(w: float):
+    """Over-relaxation factor of the ORDER_RB pressure sweep (1.0 = plain red-black Gauss-Seidel)."""
+    lib().orc_set_sor_omega(C.c_double(float(w)))
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

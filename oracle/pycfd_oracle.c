@@ -202,6 +202,12 @@ static inline void quick_cell(const double *Var, size_t kbase, const double *Ff,
     *ap_c = sum_flux * volp;
 }
 
+/* Successive over-relaxation factor of the RED-BLACK pressure sweep (north_star's "red-black-SOR"; not in the reference,
+ * whose update is omega = 1): p += omega * R/ap with R and ap exactly as in solve_pressure (LDC.py:300-310).
+ * Process-wide because the oracle is test infrastructure; 1.0 = the plain sweep. */
+static double g_sor_omega = 1.0;
+void orc_set_sor_omega(double w) { g_sor_omega = (w > 0.0) ? w : 1.0; }
+
 /* One cell of one relaxation sweep.  `src` is the array the stencil reads
  * (== Var for the in-place orders, the previous iterate for Jacobi); the new
  * value is returned, R is handed back for the residual norm.
@@ -281,6 +287,8 @@ static int inner_solve(int op, double *Var, const double *VarOld, const double *
                         if (((i + j) & 1) != colour) continue;
                         double R;
                         double nv = relax_cell(op, Var, VarOld, Ff, k, Nx, Ny, g.sI, g.P, i, j, dx, dy, dt, nu_or_rho, volp, &R);
+                        if (op == ORC_OP_PRESSURE && g_sor_omega != 1.0)
+                            nv = Var[(size_t)k * g.P + (size_t)i * g.sI + j] + g_sor_omega * (R / diff_ap(dx, dy, volp));
                         Var[(size_t)k * g.P + (size_t)i * g.sI + j] = nv;
                         rms += R * R;
                     }

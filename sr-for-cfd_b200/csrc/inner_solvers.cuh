@@ -31,6 +31,7 @@ struct SolveArgs {
     int nbands, band_rows;    // wavefront row bands
     int spin_limit;
     int guess_bias;           // first group runs guess + bias sweeps (bias <= 0 under-guesses)
+    double omega;             // RED_BLACK pressure: successive over-relaxation factor (1 = plain sweep)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -96,7 +97,9 @@ __global__ void __launch_bounds__(SYNC_THREADS) k_solve_sync(SolveArgs a) {
                     const int i = (int)(idx / K.ny) + 1, j = (int)(idx % K.ny) + 1;
                     if (((i + j) & 1) != colour) continue;
                     double R;
-                    const double nv = eval_cell<OP>(a, A, i, j, R);
+                    double nv = eval_cell<OP>(a, A, i, j, R);
+                    if (OP == OP_PRESSURE && a.omega != 1.0)         // red-black SOR: p += omega * R/ap (R as in the plain sweep)
+                        nv = __ldcg(A + (long long)i * K.pitch + j) + a.omega * (R / K.ap_d);
                     A[(long long)i * K.pitch + j] = nv;
                     acc += R * R;
                 }

@@ -46,7 +46,7 @@ static SolveArgs slab_solve_args(srcfd_handle* h, int k, int slot) {
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
     a.k = k; a.slot = slot; a.tol = h->p.inner_tol; a.max_iter = h->p.inner_max;
-    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0; a.omega = 1.0;
     return a;
 }
 static double* slab_buf(srcfd_handle* h, int k, int idx) {

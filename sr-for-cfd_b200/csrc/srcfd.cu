@@ -137,6 +137,7 @@ static int check_params(const srcfd_params* p) {
     if (p->scheme != SRCFD_SCHEME_UPWIND && p->scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
     if (p->sweep_order < 0 || p->sweep_order > 2) return fail(SRCFD_ERR_ARG, "bad sweep_order");
     if (p->inner_max < 1) return fail(SRCFD_ERR_ARG, "inner_max must be >= 1");
+    if (!(p->sor_omega >= 0.0 && p->sor_omega < 2.0)) return fail(SRCFD_ERR_ARG, "sor_omega must be in [0, 2) (0 = off)");
     if (p->sweep_order == SRCFD_ORDER_RED_BLACK && p->scheme == SRCFD_SCHEME_QUICK)
         return fail(SRCFD_ERR_ARG, "red-black order is undefined for the 9-point QUICK stencil (same-colour second neighbours)");
     return SRCFD_OK;
@@ -595,6 +596,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
     a.k = k; a.slot = slot; a.tol = h->p.inner_tol; a.max_iter = h->p.inner_max;
     a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = h->guess_bias;
+    a.omega = (h->p.sor_omega > 0.0 && op == OP_PRESSURE) ? h->p.sor_omega : 1.0;
     void* args[] = {&a};
     EvPair ev;
     if (h->timing) if (int rc = ev_begin(h, op == OP_PRESSURE ? 0 : 1, ev)) return rc;
@@ -872,7 +874,7 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
     a.k = 2; a.slot = 2; a.tol = 0.0; a.max_iter = nsweeps;
-    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0; a.omega = 1.0;
     ja.partials = h->jtb_partials;
     // boundary cells of the scratch plane must match the plane (the pass only writes interior cells)
     if (!h->jtb_ghosts_valid) {                             // they only change with the plane's own boundary cells
@@ -919,7 +921,7 @@ int srcfd_k_jacobi_commit(srcfd_handle* h) {
     a.Var = h->Var; a.VarOld = h->VarOld; a.Ff = h->Ff; a.rhs = h->rhs; a.scratch = h->scratch;
     a.partials = h->partials; a.prog = h->prog; a.ctrl = h->ctrl; a.K = h->K;
     a.k = 2; a.slot = 2; a.tol = 0.0; a.max_iter = 0;
-    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0;
+    a.nbands = h->nbands; a.band_rows = h->band_rows; a.spin_limit = h->spin_limit; a.guess_bias = 0; a.omega = 1.0;
     k_jacobi_tb_commit<<<std::max(1, h->tail_blocks / 4), 256, 0, h->stream>>>(a);
     LAUNCH_CHECK(h);
     h->launches += 1;

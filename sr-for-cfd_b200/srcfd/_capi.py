@@ -40,7 +40,8 @@ class Params(C.Structure):
         ("sweep_order", C.c_int32),
         ("device", C.c_int32),
         ("max_ctas", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("sor_omega", C.c_double),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -56,6 +56,7 @@ def _handle(Nx, Ny, **kw) -> capi.Handle:
     p.inner_max = 1000
     want_max = int(kw.get("max_iter", 1000))
     p.sweep_order = _order(kw.get("sweep_order"))
+    p.sor_omega = float(kw.get("sor_omega", 1.0) or 1.0)
     p.device = default_device
     key = (p.nx, p.ny, p.device, max(1000, want_max))
     h = _cache.get(key)
@@ -140,11 +141,12 @@ def under_relax_field(Var, VarOld, k, Nx, Ny, alpha):
     h.download(Var=Var)
 
 
-def solve_pressure(Var, Ff, Nx, Ny, dx, dy, dt, rho, volp, *, sweep_order=None, tolerance=1e-6, max_iter=1000):
-    """LDC.py:292-314."""
+def solve_pressure(Var, Ff, Nx, Ny, dx, dy, dt, rho, volp, *, sweep_order=None, tolerance=1e-6, max_iter=1000,
+                   sor_omega=1.0):
+    """LDC.py:292-314.  sor_omega (RED_BLACK order only): p += omega * R/ap, red-black SOR."""
     _chk(Var, 3, Nx, Ny, "Var"); _chk(Ff, 4, Nx, Ny, "Ff")
     h = _handle(Nx, Ny, dx=dx, dy=dy, dt=dt, rho=rho, volp=volp, sweep_order=sweep_order, tolerance=tolerance,
-                max_iter=max_iter)
+                max_iter=max_iter, sor_omega=sor_omega)
     h.upload(Var=Var, Ff=Ff)
     n, _ = h.k_solve_pressure()
     h.download(Var=Var)

@@ -81,8 +81,9 @@ class SolverSettings:
     def __init__(self, dt: float = 0.001, max_iterations: int = 100000,
                  convergence_criteria: Dict[str, float] = None, scheme: str = 'QUICK',
                  relaxation_factors: Dict[str, float] = None, *, sweep_order: str = None,
-                 inner_tolerance: float = 1e-6, inner_max_iter: int = 1000):
+                 inner_tolerance: float = 1e-6, inner_max_iter: int = 1000, sor_omega: float = 1.0):
         self.dt = dt
+        self.sor_omega = sor_omega           # opt-in: over-relaxation of the RED_BLACK pressure sweep
         self.max_iterations = max_iterations
         self.scheme = scheme
         self.convergence_criteria = convergence_criteria if convergence_criteria is not None else {
@@ -140,6 +141,7 @@ def make_params(mesh, fluid, settings, bc, case_type=None, step_height=1.0, h=2.
     order = getattr(s, 'sweep_order', 'GS_LEX')
     p.sweep_order = capi.ORDERS[order.upper()] if isinstance(order, str) else int(order)
     p.device, p.max_ctas = device, max_ctas
+    p.sor_omega = float(getattr(s, 'sor_omega', 1.0) or 1.0)
     return p
 
 

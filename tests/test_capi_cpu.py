@@ -23,13 +23,14 @@ def test_header_and_library_agree():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, f"declared in include/srcfd.h but not exported: {missing}"
     assert sorted(set(capi.SYMBOLS)) == names, "srcfd/_capi.py SYMBOLS is out of sync with the header"
-    assert L.srcfd_abi_version() == 1
+    assert L.srcfd_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():
     # int32 x2, double x6, int32 + pad, int32[12], double[12], int32 + pad, double x3, int32 + pad, double x3, double,
     # int32 x4, int32[8]  -> 4-byte members packed with natural alignment
     assert C.sizeof(capi.Params) == 8 + 48 + 8 + 48 + 96 + 8 + 24 + 8 + 24 + 8 + 16 + 32
+    assert capi.Params.sor_omega.offset == C.sizeof(capi.Params) - 32 and capi.Params.reserved.size == 24   # carved out of reserved[8]
 
 
 @pytest.mark.skipif(capi.device_count() > 0, reason="a CUDA device is present")

@@ -458,3 +458,25 @@ def test_methods_still_run_after_a_converged_solve():
     s._implicit_solve(); o.implicit_solve()
     assert not np.array_equal(s.Var, before)
     assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
+
+
+def test_red_black_sor_pressure_bit_exact_and_faster_to_tolerance():
+    """SURVEY 8f-4 (a better Poisson solver behind the same criterion): red-black SOR, p += omega * R/ap.  Bit-equal to
+    the oracle's restatement for every omega, and the same tolerance is reached in a fraction of the sweeps."""
+    from srcfd import kernels as K
+    Nx, Ny = 48, 40
+    rng = np.random.default_rng(7)
+    Var = rng.uniform(-1, 1, (3, Nx + 2, Ny + 2)); Ff = 0.01 * rng.uniform(-1, 1, (4, Nx + 2, Ny + 2))
+    dx, dy = 1.0 / Nx, 1.0 / Ny
+    counts = {}
+    try:
+        for w in (1.0, 1.5, 1.85):
+            O.set_sor_omega(w)
+            A, B = Var.copy(), Var.copy()
+            n = K.solve_pressure(A, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, sweep_order="RED_BLACK", tolerance=1e-4, max_iter=4000, sor_omega=w)
+            m = O.solve_pressure(B, Ff, Nx, Ny, dx, dy, 1e-3, 1.0, dx * dy, order=O.ORDER_RB, tolerance=1e-4, max_iter=4000)
+            assert n == m and np.array_equal(A, B), (w, n, m, np.max(np.abs(A - B)))
+            counts[w] = n
+    finally:
+        O.set_sor_omega(1.0)
+    assert counts[1.85] * 5 < counts[1.0] and counts[1.5] < counts[1.0]
