@@ -156,6 +156,11 @@ int srcfd_slab_attach_local(srcfd_handle *h, int peer_rank, srcfd_handle *peer);
 /* owned local rows (1-based, inclusive), exchanges done, bytes pushed to neighbours, blocks replayed after an overshoot */
 int srcfd_slab_info(srcfd_handle *h, int32_t *own_row0, int32_t *own_row1, int64_t *exchanges, int64_t *halo_bytes,
                     int64_t *replays);
+/* pressure solves run by the warp-streaming kernel / by the tile kernel (a rank falls back to tiles for a while when a
+ * solve sent more than 0.01 % of its warp-steps to the IEEE division routine: denormal bands of a flow started from rest),
+ * and the counts of the last solve */
+int srcfd_slab_kernel_stats(srcfd_handle *h, int64_t *stream_solves, int64_t *tile_solves, int64_t *last_retries,
+                            int64_t *last_warp_steps);
 /* refresh the halo rows of plane k from the neighbours' owned rows */
 int srcfd_slab_exchange(srcfd_handle *const *hs, int n, int k);
 int srcfd_slab_solve_pressure(srcfd_handle *const *hs, int n, int32_t *sweeps, double *last_rms);            /* LDC.py:292-314 */

@@ -32,7 +32,8 @@ struct JtbShape {
 // One pass: nsw (<= H) sweeps from plane src to plane dst; acc[t] += sum of R^2 of sweep t over this CTA's owned cells.
 template <int H>
 __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, double* __restrict__ dst, const int nsw,
-                         double* sm, double* acc, const Gs3Div& D, const int res_r0, const int res_r1) {
+                         double* sm, double* acc, const Gs3Div& D, const int res_r0, const int res_r1,
+                         unsigned long long* __restrict__ retries = nullptr) {
     constexpr int RI = JtbShape<H>::RI, RJ = JtbShape<H>::RJ;
     const Consts& K = a.K;
     double* b0 = sm;
@@ -107,6 +108,7 @@ __device__ void jtb_pass(const SolveArgs& a, const double* __restrict__ src, dou
                             bad = bad || fail;
                         }
                         if (__builtin_expect(bad, 0)) {
+                            if (retries) atomicAdd(retries, 1ull);   // four-cell groups that took the IEEE routine (the host steers by it)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const double2 o = pressure_cell3_ieee(v[q + 1], v[q + 2], v[q], cur[idx + q * RJ + 1],
@@ -230,7 +232,8 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb(JtbArgs ja) {
 template <int H>
 __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, const double* __restrict__ src, double* __restrict__ dst,
                                                                 int nsw, int res_r0, int res_r1, double* __restrict__ sums,
-                                                                unsigned* __restrict__ ticket, const int* __restrict__ done) {
+                                                                unsigned* __restrict__ ticket, const int* __restrict__ done,
+                                                                unsigned long long* __restrict__ retries) {
     const SolveArgs& a = ja.s;
     if (a.ctrl->stop) return;
     if (done && *(const volatile int*)done) return;          // slab solves: the break test was met in an earlier block
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(JTB_THREADS) k_jacobi_tb_pass(JtbArgs ja, cons
     double acc[H];
 #pragma unroll
     for (int t = 0; t < H; ++t) acc[t] = 0.0;
-    jtb_pass<H>(a, src, dst, nsw, smem, acc, D, res_r0, res_r1);
+    jtb_pass<H>(a, src, dst, nsw, smem, acc, D, res_r0, res_r1, retries);
 #pragma unroll
     for (int t = 0; t < H; ++t) {
         const double tot = block_sum(acc[t], red);
@@ -283,6 +286,282 @@ __global__ void k_jacobi_tb_commit(SolveArgs a) {
         const long long c = (idx / K.ny + 1) * K.pitch + (idx % K.ny) + 1;
         A[c] = a.scratch[c];
     }
+}
+
+// =====================================================================================================================
+// Second generation: warp-streaming temporal blocking (no shared memory, no block barrier).
+//
+// A WARP owns a strip of 64 columns (two per lane) and walks down a chunk of rows.  The NL time levels of a pass are a
+// register pipeline: at step i the warp loads row i of the source plane and then, for t = 1..NL, computes row i-t of
+// sweep t from the three most recent rows of sweep t-1, which it holds in registers (a 3-row window per level and
+// column); the left/right neighbours are the lane's other column or one shuffle away.  Row i-NL of the last sweep is
+// stored.  Nothing is staged in shared memory and no thread waits for another warp, so the per-sweep CTA barrier of
+// the tile kernel above (37 % of its warp samples) is gone and latency is hidden by the other warps of the SM.
+//   * validity: a lane within t columns of the strip edge holds garbage at sweep t (its neighbour was outside the
+//     strip), so a strip owns its 64 - 2*NL middle columns; likewise a chunk streams NL rows above and below the rows
+//     it owns.  Redundancy (64 / 56) x (RB + 8) / RB at NL = 4.
+//   * boundary cells are constant during an inner solve (hazard H6): a cell that is not interior passes its value
+//     from level to level unchanged, so ghost rows / columns need no special case and the out-of-plane lanes of an
+//     edge strip simply hold zeros;
+//   * per-sweep residual sums over owned interior cells: lane -> warp (xor shuffles) -> one partial per (sweep, unit),
+//     added up in unit order by the last CTA to finish (fixed order: deterministic);
+//   * arithmetic: pressure_cell3z, i.e. the same exact-reciprocal division sequence as above (IEEE fallback per level).
+// DRAM traffic per pass: the plane and the right-hand side read once (x redundancy), the plane written once.
+// =====================================================================================================================
+#ifndef JTB2_MINB
+#define JTB2_MINB 2
+#endif
+#ifndef JTB2_T
+#define JTB2_T 256
+#endif
+constexpr int JTB2_THREADS = JTB2_T, JTB2_WARPS = JTB2_THREADS / 32;
+
+// Second try for a pair of cells whose fast division missed its range test: zero numerators (fields at rest) are exact
+// with a select (pressure_cell3z), anything else takes the IEEE routine.  Out of line: the steady-state loop only tests.
+struct Jtb2Pair { double xA, RA, xB, RB; };
+__device__ __noinline__ Jtb2Pair jtb2_retry_pair(double cA, double dnA, double upA, double cB, double dnB, double upB, double lft,
+                                                 double rgt, double rhA, double rhB, double volp, const Gs3Div& D) {
+    Jtb2Pair o;
+    bool f1 = false, f2 = false;
+    o.xA = pressure_cell3z(cA, dnA, upA, cB, lft, rhA, volp, D, o.RA, f1);
+    o.xB = pressure_cell3z(cB, dnB, upB, rgt, cA, rhB, volp, D, o.RB, f2);
+    if (f1) { const double2 t = pressure_cell3_ieee(cA, dnA, upA, cB, lft, rhA, volp, D.dx2.b, D.dy2.b, D.apd.b); o.xA = t.x; o.RA = t.y; }
+    if (f2) { const double2 t = pressure_cell3_ieee(cB, dnB, upB, rgt, cA, rhB, volp, D.dx2.b, D.dy2.b, D.apd.b); o.xB = t.x; o.RB = t.y; }
+    return o;
+}
+
+struct Jtb2Geom {
+    int own_cols;     // 64 - 2*NL
+    int n_strips, n_chunks, RB;
+};
+
+struct Jtb2Lane {     // what a lane knows about its two columns
+    bool inA, inB;    // inside the plane (ghost columns included): loads allowed
+    bool intA, intB;  // interior column: the cell is relaxed (else its value passes through)
+    bool ownA, ownB;  // interior and owned by this strip: counted and stored
+};
+
+// Steady-state step (every level's row is an interior row that has been streamed, three rows ahead exist): no range
+// tests, and the 3-row windows / the 3 rows in flight rotate by NAME -- PH = step mod 3 is a template argument, so the
+// slot indices are compile-time and nothing is moved.  Level L keeps row rho in slot (rho - i0 + L) mod 3, which makes
+// "written this step" = PH, "centre" = PH+2, "row above" = PH+1 at every level.
+template <int NL, int PH>
+__device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], double (&wB)[NL][3], double (&rqA)[NL + 1], double (&rqB)[NL + 1],
+                                               double (&acc)[NL], double (&nA)[3], double (&nB)[3], const double*& pA,
+                                               const double*& qA, double*& oA, const int pitch, const Jtb2Lane& L, const double volp,
+                                               const Gs3Div& D, const int ra, const int rb, const int sr0, const int sr1,
+                                               const int i_valid, unsigned long long* __restrict__ retries) {
+    constexpr int NEW = PH, UP = (PH + 1) % 3, CEN = (PH + 2) % 3;
+    const double curA = nA[PH], curB = nB[PH];
+    nA[PH] = L.inA ? __ldcg(pA + 3 * pitch) : 0.0;                    // row i+3 of the plane
+    nB[PH] = L.inB ? __ldcg(pA + 3 * pitch + 1) : 0.0;
+    // right-hand side: rqX[t] = row i-1-t.  Row i is requested now and first used (as rqX[0]) one step from now.
+#pragma unroll
+    for (int t = NL - 1; t > 0; --t) { rqA[t] = rqA[t - 1]; rqB[t] = rqB[t - 1]; }
+    rqA[0] = rqA[NL]; rqB[0] = rqB[NL];
+    rqA[NL] = L.inA ? __ldg(qA) : 0.0;
+    rqB[NL] = L.inB ? __ldg(qA + 1) : 0.0;
+    pA += pitch; qA += pitch;
+    wA[0][NEW] = curA; wB[0][NEW] = curB;
+#pragma unroll
+    for (int t = 1; t <= NL; ++t) {
+        const int r = i - t;
+        const double cA = wA[t - 1][CEN], cB = wB[t - 1][CEN];
+        const double lft = __shfl_up_sync(0xffffffffu, cB, 1);
+        const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);
+        double RA, RB_;
+        bool failA = false, failB = false;
+        double xA = pressure_cell3p(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, lft, rqA[t - 1], volp, D, RA, failA);
+        double xB = pressure_cell3p(cB, wB[t - 1][NEW], wB[t - 1][UP], rgt, cA, rqB[t - 1], volp, D, RB_, failB);
+        // a miss only matters in an interior column (the out-of-plane lanes of an edge strip hold zeros and always miss)
+        // and once the level is fed by streamed rows (the first 2t steps of a chunk compute lead-in garbage)
+        if (__builtin_expect(((failA && L.intA) || (failB && L.intB)) && i - i_valid >= 2 * t, 0)) {
+            const Jtb2Pair o = jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, wB[t - 1][NEW], wB[t - 1][UP], lft, rgt,
+                                               rqA[t - 1], rqB[t - 1], volp, D);
+            xA = o.xA; RA = o.RA; xB = o.xB; RB_ = o.RB;
+            if (retries && (threadIdx.x & 31) == 0) atomicAdd(retries, 1ull);   // the host steers by this count (see l_jtb2_pass)
+        }
+        const double nvA = L.intA ? xA : cA, nvB = L.intB ? xB : cB;
+        if ((unsigned)(r - sr0) <= (unsigned)(sr1 - sr0)) {          // warp-uniform (sr1 < sr0 wraps to "never")
+            acc[t - 1] += RA * RA;                                    // per-lane sums, unmasked: a lane either owns both of its
+            acc[t - 1] += RB_ * RB_;                                  // columns or neither (else the unit takes the generic steps)
+        }
+        if (t < NL) {
+            wA[t][NEW] = nvA; wB[t][NEW] = nvB;
+        } else if ((unsigned)(r - ra) <= (unsigned)(rb - ra)) {
+            if (L.ownA) oA[0] = nvA;
+            if (L.ownB) oA[1] = nvB;
+        }
+    }
+    oA += pitch;
+}
+
+template <int NL>
+__global__ void __launch_bounds__(JTB2_THREADS, JTB2_MINB) k_jtb2_pass(JtbArgs ja, const double* __restrict__ src, double* __restrict__ dst,
+                                                                       Jtb2Geom g, int res_r0, int res_r1, double* __restrict__ partials,
+                                                                       double* __restrict__ sums, unsigned* __restrict__ ticket,
+                                                                       const int* __restrict__ done,
+                                                                       unsigned long long* __restrict__ retries) {
+    const SolveArgs& a = ja.s;
+    if (a.ctrl->stop) return;
+    if (done && *(const volatile int*)done) return;
+    __shared__ double red[32];
+    const Consts& K = a.K;
+    Gs3Div D;
+    D.dx2 = make_invdiv3(K.dx2); D.dy2 = make_invdiv3(K.dy2); D.apd = make_invdiv3(K.ap_d);
+    const double volp = K.volp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_units = g.n_strips * g.n_chunks;
+    const int pitch = K.pitch;
+    for (int u = blockIdx.x * JTB2_WARPS + warp; u < n_units; u += gridDim.x * JTB2_WARPS) {
+        const int s = u % g.n_strips, ch = u / g.n_strips;
+        const int jA = 1 + s * g.own_cols - NL + 2 * lane, jB = jA + 1;
+        const int ra = 1 + ch * g.RB, rb = min(K.nx, ra + g.RB - 1);
+        const int i_start = max(0, ra - NL), i_end = rb + NL;
+        Jtb2Lane L;
+        L.inA = jA >= 0 && jA <= K.ny + 1; L.inB = jB >= 0 && jB <= K.ny + 1;
+        L.intA = jA >= 1 && jA <= K.ny; L.intB = jB >= 1 && jB <= K.ny;
+        L.ownA = L.intA && 2 * lane >= NL && 2 * lane < NL + g.own_cols;
+        L.ownB = L.intB && 2 * lane + 1 >= NL && 2 * lane + 1 < NL + g.own_cols;
+        // a lane that owns exactly one of its two columns (odd NL, odd ny): the unit masks cell by cell in the generic steps
+        const bool split = __any_sync(0xffffffffu, L.ownA != L.ownB);
+        int sr0 = max(ra, res_r0), sr1 = min(rb, res_r1);             // rows whose residual this unit counts
+        if (sr1 < sr0) sr0 = sr1 = 0x3fffffff;                        // none: keeps the unsigned range test of the steady-state step false
+        const int i_valid = (ra - NL <= 0) ? -0x3fffffff : i_start;   // level t is fed by streamed rows from step i_valid + 2t on
+        double wA[NL][3], wB[NL][3];                                  // window of level t: rows (newest-2, newest-1, newest)
+        double rqA[NL + 1], rqB[NL + 1];                              // right-hand side of rows i-1 .. i-NL; [NL] = row i, in flight
+        double acc[NL];
+#pragma unroll
+        for (int t = 0; t < NL; ++t) {
+            acc[t] = 0.0; rqA[t] = rqB[t] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) wA[t][q] = wB[t][q] = 0.0;
+        }
+        rqA[NL] = rqB[NL] = 0.0;
+        // plane rows are requested two steps ahead of their use (three in the steady state)
+        const double* pA = src + (long long)i_start * pitch + jA;
+        const double* qA = a.rhs + (long long)i_start * pitch + jA;
+        double* oA = dst + (long long)(i_start - NL) * pitch + jA;
+        double n0A = 0.0, n0B = 0.0, n1A = 0.0, n1B = 0.0;            // plane rows i, i+1 in flight
+        if (i_start <= K.nx + 1) {
+            if (L.inA) n0A = __ldcg(pA);
+            if (L.inB) n0B = __ldcg(pA + 1);
+        }
+        if (i_start + 1 <= K.nx + 1) {
+            if (L.inA) n1A = __ldcg(pA + pitch);
+            if (L.inB) n1B = __ldcg(pA + pitch + 1);
+        }
+        // generic step: every range is tested (first / last rows of a chunk, plane edges, split units)
+        auto slow_step = [&](const int i) {
+            double curA = n0A, curB = n0B;
+            n0A = n1A; n0B = n1B;
+            n1A = n1B = 0.0;
+            if (i + 2 <= K.nx + 1) {
+                if (L.inA) n1A = __ldcg(pA + 2 * pitch);
+                if (L.inB) n1B = __ldcg(pA + 2 * pitch + 1);
+            }
+#pragma unroll
+            for (int t = NL - 1; t > 0; --t) { rqA[t] = rqA[t - 1]; rqB[t] = rqB[t - 1]; }
+            rqA[0] = rqA[NL]; rqB[0] = rqB[NL];                       // rqX[t-1] = right-hand side of row i-t
+            rqA[NL] = rqB[NL] = 0.0;
+            if (i <= K.nx + 1) {
+                if (L.inA) rqA[NL] = __ldg(qA);
+                if (L.inB) rqB[NL] = __ldg(qA + 1);
+            }
+            pA += pitch; qA += pitch;
+            wA[0][0] = wA[0][1]; wA[0][1] = wA[0][2]; wA[0][2] = curA;
+            wB[0][0] = wB[0][1]; wB[0][1] = wB[0][2]; wB[0][2] = curB;
+#pragma unroll
+            for (int t = 1; t <= NL; ++t) {
+                const int r = i - t;                                  // row computed at this level (warp-uniform)
+                double nvA = wA[t - 1][1], nvB = wB[t - 1][1];        // not interior: the value passes through
+                if (r >= i_start && r <= K.nx + 1) {
+                    const double cA = wA[t - 1][1], cB = wB[t - 1][1];
+                    const double lft = __shfl_up_sync(0xffffffffu, cB, 1);       // column jA - 1
+                    const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);     // column jB + 1
+                    if (r >= 1 && r <= K.nx) {
+                        double RA, RB_;
+                        bool f1 = false, f2 = false;
+                        double xA = pressure_cell3z(cA, wA[t - 1][2], wA[t - 1][0], cB, lft, rqA[t - 1], volp, D, RA, f1);
+                        double xB = pressure_cell3z(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D, RB_, f2);
+                        if (__builtin_expect((f1 && L.intA) || (f2 && L.intB), 0)) {
+                            const double2 o1 = pressure_cell3_ieee(cA, wA[t - 1][2], wA[t - 1][0], cB, lft, rqA[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
+                            const double2 o2 = pressure_cell3_ieee(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
+                            xA = o1.x; RA = o1.y; xB = o2.x; RB_ = o2.y;
+                        }
+                        if (L.intA) nvA = xA;
+                        if (L.intB) nvB = xB;
+                        if (r >= sr0 && r <= sr1) {
+                            acc[t - 1] += L.ownA ? RA * RA : 0.0;
+                            acc[t - 1] += L.ownB ? RB_ * RB_ : 0.0;
+                        }
+                    }
+                }
+                if (t < NL) {
+                    wA[t][0] = wA[t][1]; wA[t][1] = wA[t][2]; wA[t][2] = nvA;
+                    wB[t][0] = wB[t][1]; wB[t][1] = wB[t][2]; wB[t][2] = nvB;
+                } else if (r >= ra && r <= rb) {
+                    if (L.ownA) oA[0] = nvA;
+                    if (L.ownB) oA[1] = nvB;
+                }
+            }
+            oA += pitch;
+        };
+        // Steady-state steps need every level's row to be interior (1 <= i-NL, i-1 <= nx) and row i+3 to exist; rows above
+        // the chunk's first streamed row only produce lead-in garbage, which is never stored, counted or retried, so an
+        // interior chunk runs steady-state steps from its first row on.  Generic steps: ghost rows of the first and the
+        // last chunk of the plane, the one or two rows left over by the unroll-by-3, and units with a split lane.
+        int i = i_start;
+        const int f_lo = (i_start == 0) ? NL + 1 : i_start, f_hi = min(K.nx - 2, i_end);
+        bool steady_done = split;
+        while (i <= i_end) {
+            if (!steady_done && i >= f_lo) {
+                steady_done = true;
+                const int nfast = ((f_hi - i + 1) / 3) * 3;
+                if (nfast > 0) {
+                    double nA[3], nB[3];
+                    nA[0] = n0A; nB[0] = n0B;
+                    nA[1] = n1A; nB[1] = n1B;
+                    nA[2] = L.inA ? __ldcg(pA + 2 * pitch) : 0.0;
+                    nB[2] = L.inB ? __ldcg(pA + 2 * pitch + 1) : 0.0;
+                    for (int m = 0; m < nfast; m += 3, i += 3) {
+                        jtb2_fast_step<NL, 0>(i, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                        jtb2_fast_step<NL, 1>(i + 1, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                        jtb2_fast_step<NL, 2>(i + 2, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                    }
+                    n0A = nA[0]; n0B = nB[0];                          // rows i, i+1 for the generic steps (row i+2 is re-requested there)
+                    n1A = nA[1]; n1B = nB[1];
+                    continue;
+                }
+            }
+            slow_step(i);
+            ++i;
+        }
+#pragma unroll
+        for (int t = 0; t < NL; ++t) {
+            double v = (split || L.ownA) ? acc[t] : 0.0;             // split units masked cell by cell; else a lane owns both or none
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) partials[(size_t)t * n_units + u] = v;
+        }
+    }
+    __shared__ unsigned s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int t = 0; t < NL; ++t) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < n_units; b += blockDim.x) s += __ldcg(partials + (size_t)t * n_units + b);
+        const double all = block_sum(s, red);
+        if (threadIdx.x == 0) sums[t] = all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 }  // namespace srcfd

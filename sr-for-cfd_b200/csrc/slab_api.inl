@@ -28,6 +28,15 @@ struct SlabState {
     int64_t exchanges = 0;
     int64_t halo_bytes = 0;       // bytes this rank pushed to neighbours
     int64_t replays = 0;
+    // The streaming pressure kernel (k_jtb2_pass) is the default; a field with a band of denormal values (a cavity
+    // started from rest: the pressure front decays by ~1/4 per cell until it underflows) sends whole column strips to
+    // the IEEE division routine on every step, and a strip is one warp's work for a whole chunk.  The kernel counts
+    // those warp-steps; when they exceed 0.01 % in a solve (stragglers: the kernel waits for its slowest warp), the next solves use the tile kernel (k_jacobi_tb_pass,
+    // same bits, small 2-D work units), which counts its own trips to the IEEE routine: the streaming kernel comes
+    // back when a tile-kernel solve reports (almost) none.  A handle starts on tiles, i.e. its first solve is the probe.
+    bool use_tiles = true;
+    long long warp_steps = 0;     // of the running solve
+    int64_t tile_solves = 0, stream_solves = 0;
 };
 
 static void slab_release(srcfd_handle* h) {
@@ -160,14 +169,21 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         JtbArgs ja;
         ja.s = slab_solve_args(h, 2, 2); ja.partials = h->jtb_partials;
         for (int t = 0; t < nsw;) {
-            int m = std::min(h->jtb_H, nsw - t);
+            const bool stream = h->jtb_impl == 2 && !S->use_tiles;
+            int m = std::min(stream ? 4 : h->jtb_H, nsw - t);
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
             double* sums = S->sums + t;
             int r0 = S->own0, r1 = S->own1;
-            void* args[] = {&ja, &sp, &dp, &m, &r0, &r1, &sums, &h->jtb_ticket, &done};
-            CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
-            h->launches += 1;
+            if (stream) {
+                TRY(l_jtb2_pass(h, ja, sp, dp, m, r0, r1, sums, done, &S->sc->retries, &S->warp_steps));
+            } else {
+                unsigned long long* retries = &S->sc->retries;
+                void* args[] = {&ja, &sp, &dp, &m, &r0, &r1, &sums, &h->jtb_ticket, &done, &retries};
+                CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
+                h->launches += 1;
+                S->warp_steps += (long long)h->K.nx * h->K.ny * m / 4;   // four-cell groups relaxed
+            }
             t += m; src = dst; dst = (dst == o1) ? o2 : o1;
         }
     } else {
@@ -203,10 +219,11 @@ static int slab_sync_verdict(SlabGroup& G) {
     }
     return SRCFD_OK;
 }
-static int slab_begin(SlabGroup& G) {
+static int slab_begin(SlabGroup& G, bool new_solve = false) {
     for (int i = 0; i < G.n; ++i) {
         CK(cudaSetDevice(G[i]->dev));
-        k_slab_begin<<<1, 1, 0, G[i]->stream>>>(G[i]->slab->sc);
+        if (new_solve) G[i]->slab->warp_steps = 0;
+        k_slab_begin<<<1, 1, 0, G[i]->stream>>>(G[i]->slab->sc, new_solve ? 1 : 0);
         LAUNCH_CHECK(G[i]);
     }
     return SRCFD_OK;
@@ -222,7 +239,7 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
     const double tol = h0->p.inner_tol;
     int SB;
     if (op == OP_PRESSURE) {
-        const int H = std::max(1, h0->jtb_H);
+        const int H = 4;                                     // block sizes do not depend on which pressure kernel a rank runs
         SB = world > 1 ? (halo >= H ? (halo / H) * H : halo) : (SLAB_NS / H) * H;
     } else {
         SB = world > 1 ? std::min(SLAB_NS, (halo - 1) / NB) : SLAB_NS;
@@ -230,7 +247,7 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
     SB = std::min(SB, SLAB_NS);
     if (S0->block_cap > 0) SB = std::min(SB, S0->block_cap);
     if (SB < 1) return fail(SRCFD_ERR_ARG, "slab halo too thin for this stencil");
-    TRY(slab_begin(G));
+    TRY(slab_begin(G, true));
     for (int i = 0; i < G.n; ++i) {
         srcfd_handle* h = G[i];
         CK(cudaSetDevice(h->dev));
@@ -244,7 +261,7 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
     // Speculation: the first round runs exactly the previous outer iteration's count (its last block ends on that sweep,
     // so an unchanged count needs no replay); if the tolerance is still unmet, follow-up rounds grow from one pass.
     int want = std::min(max_iter, S0->guess[slot] > 0 ? S0->guess[slot] : max_iter);
-    int grow = op == OP_PRESSURE ? std::max(1, h0->jtb_H) : 2;
+    int grow = op == OP_PRESSURE ? 4 : 2;
     int n_final = 0, final_buf = 0;
     double rms_final = 0.0;
     for (;;) {
@@ -281,6 +298,12 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
     for (int i = 0; i < G.n; ++i) {
         srcfd_handle* h = G[i];
         CK(cudaSetDevice(h->dev));
+        if (op == OP_PRESSURE && h->jtb_impl == 2) {         // which pressure kernel the NEXT solves of this rank use (see SlabState)
+            SlabState* S = h->slab;
+            const double frac = S->warp_steps > 0 ? (double)S->sc_host->retries / (double)S->warp_steps : 0.0;
+            if (!S->use_tiles) { S->stream_solves += 1; if (frac > 1e-4) S->use_tiles = true; }
+            else { S->tile_solves += 1; if (frac < 1e-6) S->use_tiles = false; }
+        }
         if (final_buf != 0)
             CK(cudaMemcpyAsync(slab_buf(h, k, 0), slab_buf(h, k, final_buf), sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
         k_slab_finish_inner<<<1, 1, 0, h->stream>>>(h->ctrl, slot, n_final, rms_final);
@@ -368,6 +391,16 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
 #undef CKS
     S->peer_base[rank] = S->mail;
     h->bc.skip_lo = lo > 0; h->bc.skip_hi = hi > 0;
+    return SRCFD_OK;
+}
+
+int srcfd_slab_kernel_stats(srcfd_handle* h, int64_t* stream_solves, int64_t* tile_solves, int64_t* last_retries, int64_t* last_warp_steps) {
+    CKH(h);
+    if (!h->slab) return fail(SRCFD_ERR_ARG, "not a slab");
+    if (stream_solves) *stream_solves = h->slab->stream_solves;
+    if (tile_solves) *tile_solves = h->slab->tile_solves;
+    if (last_retries) *last_retries = (int64_t)h->slab->sc_host->retries;
+    if (last_warp_steps) *last_warp_steps = h->slab->warp_steps;
     return SRCFD_OK;
 }
 

@@ -94,6 +94,9 @@ struct srcfd_handle {
     unsigned* jtb_ticket = nullptr;     // last-CTA-done counter of the single-pass kernel
     bool jtb_ghosts_valid = false;      // boundary cells of the scratch plane match the pressure plane
     const void* jtb_pass_fn = nullptr;
+    int jtb_impl = 2;                   // SRCFD_JTB_IMPL: 2 = warp-streaming kernel (k_jtb2_pass), 1 = shared-memory tile kernel
+    double* jtb2_partials = nullptr;    // [4][units] per-(sweep, warp-unit) residual sums
+    size_t jtb2_units_cap = 0;
     long long* trace = nullptr;   // SRCFD_TRACE=1: per-task timestamps of the last K-sweep launch
     size_t trace_n = 0;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;   // srcfd_timer_start/stop
@@ -335,7 +338,7 @@ int srcfd_destroy(srcfd_handle* h) {
     cudaFree(h->Var); cudaFree(h->VarOld); cudaFree(h->Ff); cudaFree(h->rhs); cudaFree(h->scratch);
     cudaFree(h->partials); cudaFree(h->res_partials); cudaFree(h->hist); cudaFree(h->prog); cudaFree(h->ctrl);
     cudaFree(h->staging); cudaFree(h->halo); cudaFree(h->trace);
-    cudaFree(h->jtb_partials); cudaFree(h->jtb_sums); cudaFree(h->jtb_ticket);
+    cudaFree(h->jtb_partials); cudaFree(h->jtb_sums); cudaFree(h->jtb_ticket); cudaFree(h->jtb2_partials);
     cudaFree(h->gs3_ll); cudaFree(h->gs3_rhsS); cudaFree(h->gs3_epoch);
     cudaFree(h->sweeps1); cudaFree(h->sweeps2);
     cudaFree(h->halo2); cudaFree(h->scratch2); cudaFree(h->partials2); cudaFree(h->prog2);
@@ -399,6 +402,9 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->partials2, sizeof(double) * h->n_partials));
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
+    if (const char* e = getenv("SRCFD_JTB_IMPL")) h->jtb_impl = atoi(e);
+    h->jtb2_units_cap = (size_t)((h->p.ny + 55) / 56 + 1) * (size_t)((h->p.nx + 31) / 32 + 1);
+    CKB(cudaMalloc(&h->jtb2_partials, sizeof(double) * 4 * h->jtb2_units_cap));
     if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream));
                       CKB(cudaMalloc(&h->jtb_ticket, sizeof(unsigned))); CKB(cudaMemsetAsync(h->jtb_ticket, 0, sizeof(unsigned), h->stream)); }
     if (h->gs3) {
@@ -585,6 +591,37 @@ static int ev_drain(srcfd_handle* h) {
         h->ev_free.push_back(ev);
     }
     h->ev_pending.clear();
+    return SRCFD_OK;
+}
+
+// One pass (nsw <= 4 sweeps) of the warp-streaming Jacobi kernel from plane src to plane dst; per-sweep sums of R^2 over
+// rows [r0, r1] into sums[0..nsw).  The row chunk is sized so that every warp slot of the GPU gets about two units.
+static int l_jtb2_pass(srcfd_handle* h, const JtbArgs& ja, const double* src, double* dst, int nsw, int r0, int r1, double* sums,
+                       const int* done, unsigned long long* retries, long long* warp_steps) {
+    if (nsw < 1 || nsw > 4) return fail(SRCFD_ERR_ARG, "jtb2: 1..4 sweeps per pass");
+    Jtb2Geom g;
+    g.own_cols = 64 - 2 * nsw;
+    g.n_strips = (h->K.ny + g.own_cols - 1) / g.own_cols;
+    const int slots = h->num_sms * 2 * JTB2_WARPS;
+    // one unit per warp slot when the rows allow chunks of >= 64 rows (fewer, longer units: less lead-in redundancy)
+    int chunks = std::max(1, slots / g.n_strips);
+    int RB = std::max(64, (h->K.nx + chunks - 1) / chunks);
+    if (h->K.nx < 64 * chunks) RB = std::max(32, (h->K.nx + 2 * chunks - 1) / (2 * chunks));   // small planes: shorter chunks, more warps
+    if (const char* e = getenv("SRCFD_JTB2_RB")) RB = std::max(1, atoi(e));
+    g.RB = RB; g.n_chunks = (h->K.nx + RB - 1) / RB;
+    const long long units = (long long)g.n_strips * g.n_chunks;
+    if ((size_t)units > h->jtb2_units_cap) return fail(SRCFD_ERR_ARG, "jtb2: partial-sum buffer too small");
+    const int grid = (int)std::max<long long>(1, std::min<long long>((units + JTB2_WARPS - 1) / JTB2_WARPS, (long long)h->num_sms * 2));
+    const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
+    const dim3 gd(std::min(grid, cap));
+    switch (nsw) {
+        case 1: k_jtb2_pass<1><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
+        case 2: k_jtb2_pass<2><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
+        case 3: k_jtb2_pass<3><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
+        default: k_jtb2_pass<4><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
+    }
+    LAUNCH_CHECK(h);
+    if (warp_steps) *warp_steps += units * (long long)(g.RB + 2 * nsw) * nsw;
     return SRCFD_OK;
 }
 
@@ -887,7 +924,8 @@ int srcfd_k_jacobi_pass(srcfd_handle* h, int nsweeps, int own_row0, int own_row1
     const double* src = h->Var + 2 * (size_t)h->K.plane;
     double* dst = h->scratch;
     const int* done = nullptr;
-    void* args[] = {&ja, &src, &dst, &nsweeps, &own_row0, &own_row1, &sums_dev, &h->jtb_ticket, &done};
+    unsigned long long* retries = nullptr;
+    void* args[] = {&ja, &src, &dst, &nsweeps, &own_row0, &own_row1, &sums_dev, &h->jtb_ticket, &done, &retries};
     CK(cudaLaunchKernel(h->jtb_pass_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), args, h->jtb_smem, h->stream));
     h->launches += 1;
     if (commit) {

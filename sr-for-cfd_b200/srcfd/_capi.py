@@ -69,7 +69,7 @@ SYMBOLS = [
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
     "srcfd_k_solve_pressure", "srcfd_jacobi_pass_max", "srcfd_k_jacobi_pass", "srcfd_k_jacobi_commit", "srcfd_jacobi_sums_ptr", "srcfd_k_jacobi_snapshot", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
     "srcfd_coarse_smem_bytes", "srcfd_coarse_solve_batch",
-    "srcfd_slab_configure", "srcfd_slab_export", "srcfd_slab_attach_ipc", "srcfd_slab_attach_local", "srcfd_slab_info",
+    "srcfd_slab_configure", "srcfd_slab_export", "srcfd_slab_attach_ipc", "srcfd_slab_attach_local", "srcfd_slab_info", "srcfd_slab_kernel_stats",
     "srcfd_slab_exchange", "srcfd_slab_solve_pressure", "srcfd_slab_solve_momentum", "srcfd_slab_step",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
     "srcfd_sr_last_error", "srcfd_sr_create", "srcfd_sr_destroy", "srcfd_sr_set_encoder", "srcfd_sr_set_decoder",

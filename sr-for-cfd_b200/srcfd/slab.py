@@ -205,6 +205,12 @@ class GpuSlab:
         self.capi.check(self.capi.lib().srcfd_slab_info(self.h._h, C.byref(r0), C.byref(r1), C.byref(ex), C.byref(hb), C.byref(rp)))
         return dict(own_row0=r0.value, own_row1=r1.value, exchanges=ex.value, halo_bytes=hb.value, replays=rp.value)
 
+    def kernel_stats(self) -> dict:
+        import ctypes as C
+        a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self.capi.check(self.capi.lib().srcfd_slab_kernel_stats(self.h._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(stream_solves=a.value, tile_solves=b.value, last_retries=c.value, last_warp_steps=d.value)
+
     def export_blob(self) -> bytes:
         import ctypes as C
         buf = (C.c_ubyte * 64)()

@@ -85,7 +85,8 @@ if outer > 0:
     st1 = s2.h.status()
     sw = (st1["total_sweeps"] - st0["total_sweeps"]).astype(np.int64)
     out["outer"] = {"iterations": outer, "ms_per_iteration": ms2 / outer, "inner_sweeps": sw.tolist(),
-                    "value": n * n * float(sw.sum()) / ms2 / 1e6, "unit": "GLUP/s", "rms": st1["rms"].tolist()}
+                    "value": n * n * float(sw.sum()) / ms2 / 1e6, "unit": "GLUP/s", "rms": st1["rms"].tolist(),
+                    "kernel_stats": s2.kernel_stats()}
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
