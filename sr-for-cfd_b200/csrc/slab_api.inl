@@ -35,6 +35,7 @@ struct SlabState {
     // same bits, small 2-D work units), which counts its own trips to the IEEE routine: the streaming kernel comes
     // back when a tile-kernel solve reports (almost) none.  A handle starts on tiles, i.e. its first solve is the probe.
     bool use_tiles = true;
+    bool force_stream = false;    // SRCFD_JTB2_FORCE (experiments): streaming kernel on thin slabs too
     long long warp_steps = 0;     // of the running solve
     int64_t tile_solves = 0, stream_solves = 0;
 };
@@ -169,7 +170,11 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         JtbArgs ja;
         ja.s = slab_solve_args(h, 2, 2); ja.partials = h->jtb_partials;
         for (int t = 0; t < nsw;) {
-            const bool stream = h->jtb_impl == 2 && !S->use_tiles;
+            // the streaming kernel wants one >= 64-row chunk per warp slot (measured: 4096 columns x 2048+ rows per GPU
+            // 210-280 GLUP/s against 182-200 for the tile kernel; 544 rows per GPU 700 against 805-930): thin slabs keep tiles
+            const int strips4 = (h->K.ny + 55) / 56, slots = h->num_sms * 2 * JTB2_WARPS;
+            const bool roomy = S->force_stream || h->K.nx >= 64 * std::max(1, slots / strips4);
+            const bool stream = h->jtb_impl == 2 && !S->use_tiles && roomy;
             int m = std::min(stream ? 4 : h->jtb_H, nsw - t);
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
@@ -373,6 +378,7 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     S->lo = lo; S->hi = hi; S->own0 = lo + 1; S->own1 = lo + n_own;
     S->guess[2] = h->p.inner_max;
     if (const char* e = getenv("SRCFD_SLAB_BLOCK")) S->block_cap = atoi(e);
+    if (const char* e = getenv("SRCFD_JTB2_FORCE")) S->force_stream = atoi(e) != 0;
     S->mail_bytes = slab_mail_bytes(std::max(1, S->halo), h->K.pitch);
     auto bail = [&](int rc) { std::string keep = g_err; slab_release(h); g_err = keep; return rc; };
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(SRCFD_ERR_CUDA); } } while (0)
