@@ -226,6 +226,12 @@ int srcfd_sr_encode(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float 
 int srcfd_sr_decode(srcfd_sr *h, const float *z /* (B,50) */, int B, float *out /* (B,400,400,1) */);
 /* SuperResolutionAE.call (PyCFD_ML_accelerated.py:686-689) */
 int srcfd_sr_predict(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float *out /* (B,400,400,1) */);
+/* ml_super_resolution's per-field pipeline (PyCFD_ML_accelerated.py:841-876 / bfs_ml_accelerated.py:1084-1134) for B
+ * coarse fields in one call: [blend of the training statistics with the field's own mean/std when adaptive != 0,
+ * bfs_ml_accelerated.py:1090-1100] -> standardize_with_stats -> encoder_10 -> decoder_400 -> inverse_standardize ->
+ * NaN/Inf guard, all on the device.  x (B,10,10) float32; stats (B,4) float64 = {mean_lr, std_lr, mean_hr, std_hr} per
+ * field; out (B,400,400) float32.  (The aspect-ratio spline resampling around it stays with the caller.) */
+int srcfd_sr_super_resolve(srcfd_sr *h, const float *x, int B, const double *stats, int adaptive, double blend, float *out);
 /* decoder on device-resident latents/outputs (cudaMalloc'ed by the caller); *ms = CUDA-event time of the batch */
 int srcfd_sr_decode_device(srcfd_sr *h, uint64_t z_dev, int B, uint64_t out_dev, double *ms);
 /* 0 = fp32 CUDA cores (default; the parity path), 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers */

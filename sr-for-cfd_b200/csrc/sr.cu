@@ -179,6 +179,42 @@ __global__ void k_conv2d_transpose(const float* __restrict__ in, const float* __
     out[t] = act ? swishf(acc) : acc;
 }
 
+// ---- pre / post of ml_super_resolution (LDC.py:841-876, BFS.py:1084-1134) on the device ----------------------------------
+// stats per field: {mean_lr, std_lr, mean_hr, std_hr}.  One block per field: optional blend of the training statistics
+// with the field's own mean / std (BFS.py:1090-1100, np.mean / np.std over the 100 coarse values), then
+// standardize_with_stats (LDC.py:665-668: (x - mean) / std, std == 0 -> 1e-8) in float32.
+__global__ void k_sr_pre(const float* __restrict__ x, const double* __restrict__ stats, int adaptive, double blend,
+                         float* __restrict__ xs) {
+    __shared__ double red[128];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float v = t < 100 ? x[(size_t)b * 100 + t] : 0.f;
+    double mean = stats[4 * b + 0], sd = stats[4 * b + 1];
+    if (adaptive) {
+        red[t] = t < 100 ? (double)v : 0.0;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+        const double m = red[0] / 100.0;
+        __syncthreads();
+        const double d = t < 100 ? (double)v - m : 0.0;
+        red[t] = d * d;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+        const double in_sd = sqrt(red[0] / 100.0);
+        mean = (1.0 - blend) * mean + blend * (double)(float)m;
+        sd = (1.0 - blend) * sd + blend * fmax((double)(float)in_sd, 1e-8);
+    }
+    if (sd == 0.0) sd = 1e-8;
+    if (t < 100) xs[(size_t)b * 100 + t] = (v - (float)mean) / (float)sd;
+}
+// inverse_standardize (LDC.py:671-673: pred * std_hr + mean_hr) and the NaN/Inf guard (LDC.py:869-876), in place.
+__global__ void k_sr_post(float* __restrict__ y, const double* __restrict__ stats, long long per, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        const float v = y[i] * (float)stats[4 * b + 3] + (float)stats[4 * b + 2];
+        y[i] = (isnan(v) || isinf(v)) ? 0.f : v;
+    }
+}
+
 struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; };
 
 }  // namespace
@@ -197,6 +233,8 @@ struct srcfd_sr {
     __nv_bfloat16* actbf[6] = {nullptr};   // bf16 activations of layers 1..5 (index = layer) for one chunk
     int* tc_err = nullptr;
     FinalConvW fcw;                    // host copy of the last layer's 72 weights + bias (kernel argument)
+    double* stats_dev = nullptr;       // per-field {mean_lr, std_lr, mean_hr, std_hr} of srcfd_sr_super_resolve
+    int stats_cap = 0;
 };
 
 namespace {
@@ -353,7 +391,7 @@ int srcfd_sr_destroy(srcfd_sr* h) {
     for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
     for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); }
     for (int i = 0; i < 6; ++i) cudaFree(h->actbf[i]);
-    cudaFree(h->tc_err);
+    cudaFree(h->tc_err); cudaFree(h->stats_dev);
     for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
     cudaFree(h->zin); cudaFree(h->xin);
     cudaEventDestroy(h->ea); cudaEventDestroy(h->eb);
@@ -446,6 +484,39 @@ int srcfd_sr_predict(srcfd_sr* h, const float* x, int B, float* out) {
     if (!h || !x || !out || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
     if (!h->has_enc || !h->has_dec) return sr_fail(SRCFD_ERR_ARG, "encoder/decoder weights not set");
     return sr_run(h, x, nullptr, B, nullptr, out);
+}
+// ml_super_resolution's per-field pipeline for B fields in ONE call, everything between the two host copies on the device:
+// [adaptive statistics] -> standardize -> encoder_10 -> decoder_400 -> inverse standardize -> NaN/Inf guard.
+int srcfd_sr_super_resolve(srcfd_sr* h, const float* x, int B, const double* stats, int adaptive, double blend, float* out) {
+    if (!h || !x || !out || !stats || B < 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    if (!h->has_enc || !h->has_dec) return sr_fail(SRCFD_ERR_ARG, "encoder/decoder weights not set");
+    SRCK(cudaSetDevice(h->dev));
+    const int CH = std::min(B, 128);
+    if (int rc = ensure_chunk(h, CH)) return rc;
+    if (h->stats_cap < CH) {
+        cudaFree(h->stats_dev); h->stats_dev = nullptr; h->stats_cap = 0;
+        SRCK(cudaMalloc(&h->stats_dev, sizeof(double) * 4 * (size_t)CH));
+        h->stats_cap = CH;
+    }
+    float* zdev = h->zin + (size_t)h->chunk * 128;
+    for (int b0 = 0; b0 < B; b0 += CH) {
+        const int nb = std::min(CH, B - b0);
+        float* xraw = h->act[6];                     // staging: raw coarse fields, then (behind them) the standardized ones
+        float* xstd = h->act[6] + (size_t)nb * 100;
+        SRCK(cudaMemcpyAsync(xraw, x + (size_t)b0 * 100, (size_t)nb * 100 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        SRCK(cudaMemcpyAsync(h->stats_dev, stats + (size_t)b0 * 4, (size_t)nb * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        k_sr_pre<<<nb, 128, 0, h->stream>>>(xraw, h->stats_dev, adaptive, blend, xstd);
+        h->launches += 1;
+        if (int rc = run_encoder(h, xstd, nb, zdev)) return rc;
+        if (int rc = run_decoder(h, zdev, nb, h->act[6])) return rc;
+        const long long n = (long long)nb * 160000;
+        k_sr_post<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, h->stream>>>(h->act[6], h->stats_dev, 160000, n);
+        h->launches += 1;
+        SRCK(cudaGetLastError());
+        SRCK(cudaMemcpyAsync(out + (size_t)b0 * 160000, h->act[6], (size_t)nb * 160000 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        SRCK(cudaStreamSynchronize(h->stream));
+    }
+    return SRCFD_OK;
 }
 // Throughput entry: latents and outputs resident in HBM (device pointers), whole batch, CUDA-event timed.
 int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev, double* ms) {

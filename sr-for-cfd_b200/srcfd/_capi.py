@@ -73,7 +73,7 @@ SYMBOLS = [
     "srcfd_slab_exchange", "srcfd_slab_solve_pressure", "srcfd_slab_solve_momentum", "srcfd_slab_step",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
     "srcfd_sr_last_error", "srcfd_sr_create", "srcfd_sr_destroy", "srcfd_sr_set_encoder", "srcfd_sr_set_decoder",
-    "srcfd_sr_encode", "srcfd_sr_decode", "srcfd_sr_predict", "srcfd_sr_decode_device", "srcfd_sr_launch_count",
+    "srcfd_sr_encode", "srcfd_sr_decode", "srcfd_sr_predict", "srcfd_sr_super_resolve", "srcfd_sr_decode_device", "srcfd_sr_launch_count",
     "srcfd_sr_set_precision", "srcfd_sr_tc_error", "srcfd_sr_debug_convT_tc",
 ]
 

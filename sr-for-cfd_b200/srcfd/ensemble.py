@@ -132,13 +132,26 @@ def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optio
 
 
 def warm_stage(cases: Sequence[CaseSpec], sr_files: dict, device: int = 0) -> List[Optional[np.ndarray]]:
-    """Warm start of a whole share of cases: ONE launch for every coarse solve (coarse_stage), then the SR passes back
-    to back on the calling thread (an Encoder/Decoder handle serves one caller at a time)."""
+    """Warm start of a whole share of cases: ONE launch for every coarse solve (coarse_stage), then ONE batched SR call
+    per case family (3 fields per case; statistics, both networks and the clean-up on the device)."""
     out: List[Optional[np.ndarray]] = [None] * len(cases)
     warm = [i for i, c in enumerate(cases) if c.warm_start]
     coarse = coarse_stage([cases[i] for i in warm], device, 10, sr_files.get("coarse_iterations", 2000))
-    for i, f in zip(warm, coarse):
-        out[i] = warm_start_fields(cases[i], sr_files, f)
+    # one batched SR call per case family (the BFS cases share the aspect-ratio and adaptive-statistics settings)
+    from . import bfs, ldc
+    for kind_is_bfs, wf in ((False, ldc._wf), (True, bfs._wf)):
+        idx = [(i, f) for i, f in zip(warm, coarse) if (cases[i].kind == "bfs") == kind_is_bfs]
+        if not idx:
+            continue
+        by_dim = {}
+        for i, f in idx:
+            by_dim.setdefault(cases[i].nx, []).append((i, f))
+        for nx, grp in by_dim.items():
+            kw = dict(use_aspect_ratio_correction=True, lx=10.0, ly=3.0) if kind_is_bfs else {}
+            hr = wf.ml_super_resolution_batch([f for _, f in grp], 10, nx, sr_files["stats"], sr_files["encoder"],
+                                              sr_files["decoder"], **kw)
+            for (i, _), h in zip(grp, hr):
+                out[i] = np.stack([np.asarray(h[c], dtype=np.float32) for c in "uvp"])
     return out
 
 

@@ -182,6 +182,20 @@ def predict(encoder: Encoder, decoder: Decoder, x) -> np.ndarray:
     return out
 
 
+def super_resolve(encoder: Encoder, decoder: Decoder, x, stats, adaptive: bool = False, blend: float = 0.3) -> np.ndarray:
+    """The per-field pipeline of ml_super_resolution for B fields in one library call (device-side statistics blend,
+    standardisation, encoder, decoder, inverse standardisation, NaN/Inf guard).  x (B,10,10); stats (B,4) =
+    {mean_lr, std_lr, mean_hr, std_hr}; returns (B,400,400) float32."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 10, 10)
+    st = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1, 4)
+    assert st.shape[0] == x.shape[0] and encoder.device == decoder.device
+    encoder._bind(); h = decoder._bind()
+    out = np.empty((x.shape[0], 400, 400), dtype=np.float32)
+    _sr_check(capi.lib().srcfd_sr_super_resolve(h, x.ctypes.data_as(_fp), C.c_int(x.shape[0]), st.ctypes.data_as(C.POINTER(C.c_double)),
+                                                C.c_int(int(bool(adaptive))), C.c_double(float(blend)), out.ctypes.data_as(_fp)))
+    return out
+
+
 def decode_device(decoder: Decoder, z_dev_ptr: int, B: int, out_dev_ptr: int) -> float:
     """Decoder on device-resident buffers; returns the CUDA-event time in ms (throughput benchmark)."""
     ms = C.c_double(0.0)

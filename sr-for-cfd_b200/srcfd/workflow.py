@@ -139,33 +139,52 @@ class _Workflow:
     def ml_super_resolution(self, coarse_fields, lr_dim, hr_dim, stats_file, encoder_file, decoder_file,
                             use_aspect_ratio_correction=False, lx=1.0, ly=1.0, use_adaptive_normalization=None,
                             blend_factor=0.3):
+        return self.ml_super_resolution_batch([coarse_fields], lr_dim, hr_dim, stats_file, encoder_file, decoder_file,
+                                              use_aspect_ratio_correction, lx, ly, use_adaptive_normalization,
+                                              blend_factor)[0]
+
+    def ml_super_resolution_batch(self, coarse_list, lr_dim, hr_dim, stats_file, encoder_file, decoder_file,
+                                  use_aspect_ratio_correction=False, lx=1.0, ly=1.0, use_adaptive_normalization=None,
+                                  blend_factor=0.3):
+        """ml_super_resolution (LDC.py:764-879 / BFS.py:979-1137) for a LIST of cases: the u, v, p fields of every case go
+        through ONE library call (3 x cases fields; the reference runs three batch-1 predicts per case) in which the
+        statistics blend, the standardisation, both networks, the inverse standardisation and the NaN/Inf guard all run
+        on the device (srcfd_sr_super_resolve).  Only the aspect-ratio spline resampling stays on the host (scipy)."""
         from . import sr
         if use_adaptive_normalization is None:
             use_adaptive_normalization = self.bfs        # BFS.py:984 defaults it on, LDC.py has none
-        fields_for_ml = coarse_fields
-        if self.bfs and use_aspect_ratio_correction and (lx != ly):
-            fields_for_ml = reshape_rectangular_to_square(coarse_fields, lr_dim, lr_dim, lx, ly)
+        reshape = self.bfs and use_aspect_ratio_correction and (lx != ly)
         stats_lr, stats_hr = load_stats(stats_file, lr_dim, hr_dim)
-        model = SuperResolutionAE(sr.load_model(encoder_file), sr.load_model(decoder_file))
-        hr_fields = {}
-        for c in 'uvp':
-            x_lr_raw = np.asarray(fields_for_ml[c]).astype(np.float32)
-            mean_lr, std_lr = stats_lr[c]
-            mean_hr, std_hr = stats_hr[c]
-            if self.bfs and use_adaptive_normalization:          # BFS.py:1090-1100
-                input_mean, input_std = np.mean(x_lr_raw), np.std(x_lr_raw)
-                mean_lr = (1 - blend_factor) * mean_lr + blend_factor * input_mean
-                std_lr = (1 - blend_factor) * std_lr + blend_factor * max(input_std, 1e-8)
-            x = standardize_with_stats(x_lr_raw, mean_lr, std_lr)
-            x = np.expand_dims(x, axis=(0, -1))
-            pred = model.predict(x, verbose=0)[0, ..., 0]
-            pred = inverse_standardize(pred, mean_hr, std_hr)
-            if np.isnan(pred).any() or np.isinf(pred).any():     # LDC.py:869-876
-                pred = np.nan_to_num(pred, nan=0.0, posinf=0.0, neginf=0.0)
-            hr_fields[c] = pred
-        if self.bfs and use_aspect_ratio_correction and (lx != ly):
-            hr_fields = reshape_square_to_rectangular(hr_fields, hr_dim, hr_dim, lx, ly)
-        return hr_fields
+        enc, dec = sr.load_model(encoder_file), sr.load_model(decoder_file)
+        adaptive = bool(self.bfs and use_adaptive_normalization)
+        xs, st = [], []
+        for coarse_fields in coarse_list:
+            f = reshape_rectangular_to_square(coarse_fields, lr_dim, lr_dim, lx, ly) if reshape else coarse_fields
+            for c in 'uvp':
+                xs.append(np.asarray(f[c]).astype(np.float32))
+                st.append([stats_lr[c][0], stats_lr[c][1], stats_hr[c][0], stats_hr[c][1]])
+        if isinstance(enc, sr.Encoder) and isinstance(dec, sr.Decoder):
+            pred = sr.super_resolve(enc, dec, np.stack(xs), np.asarray(st, dtype=np.float64), adaptive, blend_factor)
+        else:                                            # foreign model objects: the reference's statement sequence on the host
+            model = SuperResolutionAE(enc, dec)
+            pred = np.empty((len(xs), hr_dim, hr_dim), dtype=np.float32)
+            for i, (x_lr_raw, (mean_lr, std_lr, mean_hr, std_hr)) in enumerate(zip(xs, st)):
+                if adaptive:                             # BFS.py:1090-1100
+                    input_mean, input_std = np.mean(x_lr_raw), np.std(x_lr_raw)
+                    mean_lr = (1 - blend_factor) * mean_lr + blend_factor * input_mean
+                    std_lr = (1 - blend_factor) * std_lr + blend_factor * max(input_std, 1e-8)
+                x = np.expand_dims(standardize_with_stats(x_lr_raw, mean_lr, std_lr), axis=(0, -1))
+                p = inverse_standardize(model.predict(x, verbose=0)[0, ..., 0], mean_hr, std_hr)
+                if np.isnan(p).any() or np.isinf(p).any():   # LDC.py:869-876
+                    p = np.nan_to_num(p, nan=0.0, posinf=0.0, neginf=0.0)
+                pred[i] = p
+        out = []
+        for n in range(len(coarse_list)):
+            hr_fields = {c: pred[3 * n + k] for k, c in enumerate('uvp')}
+            if reshape:
+                hr_fields = reshape_square_to_rectangular(hr_fields, hr_dim, hr_dim, lx, ly)
+            out.append(hr_fields)
+        return out
 
     # ---- step 3: fine solve from the SR field (LDC.py:882-959 / BFS.py:1140-1234) ---------------
     def run_fine_simulation_with_ml_init(self, Re, nx, ny, ml_initial_fields, dt=None, scheme=None,

@@ -123,3 +123,38 @@ def test_final_conv_on_tensor_cores_matches_cuda_core_kernel():
     # borders and tile seams included: rows / columns at 0, 127|128, 399 are no worse than the interior
     for sl in (np.s_[:, 0], np.s_[:, 399], np.s_[:, :, 0], np.s_[:, :, 399], np.s_[:, :, 127:129], np.s_[:, 7:9]):
         assert err[sl].max() <= 4e-3 * scale
+
+
+def test_super_resolve_device_pipeline(golden_dir):
+    """srcfd_sr_super_resolve: statistics blend, standardisation, inverse standardisation and the NaN/Inf guard on the
+    device, many fields per call -- against the reference's host statements around the same (GPU) networks."""
+    from srcfd import sr
+    from srcfd.workflow import standardize_with_stats, inverse_standardize
+    enc = sr.load_model(os.path.join(golden_dir, "encoder10_multiBC.h5"))
+    dec = sr.synthetic_decoder(0)
+    rng = np.random.default_rng(11)
+    B = 7
+    x = (0.3 * rng.standard_normal((B, 10, 10)) + rng.uniform(-1, 1, (B, 1, 1))).astype(np.float32)
+    stats = np.stack([rng.uniform(-0.2, 0.2, B), rng.uniform(0.1, 0.5, B), rng.uniform(-0.1, 0.1, B), rng.uniform(0.2, 0.6, B)], axis=1)
+    x[3] = 0.25                                            # constant field: its own std is 0 -> max(std, 1e-8)
+    stats[4, 1] = 0.0                                      # zero training std -> 1e-8 when not blended
+    stats[5, 3] = np.inf                                   # overflow in the inverse standardisation -> the guard writes zeros
+    for adaptive in (False, True):
+        got = sr.super_resolve(enc, dec, x, stats, adaptive, 0.3)
+        assert got.shape == (B, 400, 400) and got.dtype == np.float32
+        for b in range(B):
+            m, s = stats[b, 0], stats[b, 1]
+            if adaptive:
+                m = 0.7 * m + 0.3 * np.mean(x[b]); s = 0.7 * s + 0.3 * max(np.std(x[b]), 1e-8)
+            xn = standardize_with_stats(x[b], np.float32(m), np.float32(s if s != 0 else 1e-8))
+            y = sr.predict(enc, dec, xn[None, ..., None])[0, ..., 0]
+            ref = inverse_standardize(y, np.float32(stats[b, 2]), np.float32(stats[b, 3]))
+            ref = np.nan_to_num(ref, nan=0.0, posinf=0.0, neginf=0.0) if not np.isfinite(ref).all() else ref
+            if b == 5:
+                assert np.isfinite(got[b]).all() and np.count_nonzero(got[b]) < got[b].size // 2
+                continue
+            if b == 4 and not adaptive:
+                assert np.isfinite(got[b]).all()           # 1e-8 divisor: huge but finite inputs, nothing to compare closely
+                continue
+            np.testing.assert_allclose(got[b], ref, rtol=2e-4, atol=2e-4 * max(1.0, float(np.max(np.abs(ref)))))
+    assert sr.launch_count() > 0
