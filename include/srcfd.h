@@ -33,7 +33,9 @@ enum {
     SRCFD_ORDER_GS_LEX = 0,   /* reference order: in-place lexicographic Gauss-Seidel (numba, 1 thread),  */
                               /* run as a pipelined wavefront -- results bit-identical to the reference  */
     SRCFD_ORDER_JACOBI = 1,   /* every cell from the previous iterate                                     */
-    SRCFD_ORDER_RED_BLACK = 2 /* in-place two-colour sweep                                                */
+    SRCFD_ORDER_RED_BLACK = 2,/* in-place two-colour sweep                                                */
+    SRCFD_ORDER_RB_JACOBI = 3 /* pressure: red-black (SOR with srcfd_params.sor_omega); momentum: Jacobi.  The   */
+                              /* combination north_star names ("Jacobi/red-black-SOR sweeps"); works with QUICK   */
 };
 enum { SRCFD_BC_DIRICHLET = 0, SRCFD_BC_NEUMANN = 1 };              /* _get_bc_arrays, LDC.py:351-375   */
 

@@ -25,6 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libpycfd_oracle.so")
 
 ORDER_GS_LEX, ORDER_JACOBI, ORDER_RB, ORDER_GS_OMP = 0, 1, 2, 3
+ORDER_RB_JACOBI = 4      # composed solver only: momentum Jacobi, pressure red-black (SOR factor via set_sor_omega)
 SCHEME_UPWIND, SCHEME_QUICK = 0, 1
 
 

@@ -386,21 +386,23 @@ void orc_initialize_fields(const orc_params *p, double *Var, double *VarOld, dou
  * inner sweep counts (u, v, p). */
 void orc_implicit_solve(const orc_params *p, double *Var, double *VarOld, double *Ff,
                         double *residual, int32_t *sweeps) {
+    /* order 4 (RB_JACOBI): momentum in Jacobi order, pressure red-black (with the SOR factor when one is set) */
+    const int mo = p->order == 4 ? ORC_ORDER_JACOBI : p->order, po = p->order == 4 ? 2 : p->order;
     residual[0] = residual[1] = residual[2] = 0.0;
     for (int k = 0; k < 2; ++k) {
         int n;
         if (p->scheme == ORC_SCHEME_QUICK)
             n = orc_solve_momentum_quick(Var, VarOld, Ff, k, p->Nx, p->Ny, p->dx, p->dy, p->dt, p->nu,
-                                         p->volp, p->order, p->inner_tol, p->inner_max, NULL, NULL);
+                                         p->volp, mo, p->inner_tol, p->inner_max, NULL, NULL);
         else
             n = orc_solve_momentum_upwind(Var, VarOld, Ff, k, p->Nx, p->Ny, p->dx, p->dy, p->dt, p->nu,
-                                          p->volp, p->order, p->inner_tol, p->inner_max, NULL, NULL);
+                                          p->volp, mo, p->inner_tol, p->inner_max, NULL, NULL);
         if (sweeps) sweeps[k] = n;
         if (p->use_relax) orc_under_relax_field(Var, VarOld, k, p->Nx, p->Ny, p->alpha[k]);
         orc_apply_bc_wrapper(p, Var, k);
     }
     orc_linear_interpolation(Var, Ff, p->Nx, p->Ny, p->dx, p->dy);
-    int n = orc_solve_pressure(Var, Ff, p->Nx, p->Ny, p->dx, p->dy, p->dt, p->rho, p->volp, p->order,
+    int n = orc_solve_pressure(Var, Ff, p->Nx, p->Ny, p->dx, p->dy, p->dt, p->rho, p->volp, po,
                                p->inner_tol, p->inner_max, NULL, NULL);
     if (sweeps) sweeps[2] = n;
     if (p->use_relax) orc_under_relax_field(Var, VarOld, 2, p->Nx, p->Ny, p->alpha[2]);

@@ -138,7 +138,7 @@ static int check_params(const srcfd_params* p) {
     if (!p) return fail(SRCFD_ERR_ARG, "null params");
     if (p->nx < 1 || p->ny < 1) return fail(SRCFD_ERR_ARG, "nx, ny must be >= 1");
     if (p->scheme != SRCFD_SCHEME_UPWIND && p->scheme != SRCFD_SCHEME_QUICK) return fail(SRCFD_ERR_ARG, "bad scheme");
-    if (p->sweep_order < 0 || p->sweep_order > 2) return fail(SRCFD_ERR_ARG, "bad sweep_order");
+    if (p->sweep_order < 0 || p->sweep_order > 3) return fail(SRCFD_ERR_ARG, "bad sweep_order");
     if (p->inner_max < 1) return fail(SRCFD_ERR_ARG, "inner_max must be >= 1");
     if (!(p->sor_omega >= 0.0 && p->sor_omega < 2.0)) return fail(SRCFD_ERR_ARG, "sor_omega must be in [0, 2) (0 = off)");
     if (p->sweep_order == SRCFD_ORDER_RED_BLACK && p->scheme == SRCFD_SCHEME_QUICK)
@@ -637,7 +637,10 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
     void* args[] = {&a};
     EvPair ev;
     if (h->timing) if (int rc = ev_begin(h, op == OP_PRESSURE ? 0 : 1, ev)) return rc;
-    if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
+    // RB_JACOBI: red-black (SOR) for the 5-point pressure stencil, Jacobi for the momentum stencils (QUICK is 9-point)
+    const int order = h->p.sweep_order == SRCFD_ORDER_RB_JACOBI ? (op == OP_PRESSURE ? SRCFD_ORDER_RED_BLACK : SRCFD_ORDER_JACOBI)
+                                                                : h->p.sweep_order;
+    if (order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2 && op == OP_PRESSURE && h->gs3 && !pair) {
         Gs3Args g3;
         g3.s = a; g3.K = h->gs3_K; g3.ND = h->gs3_ND; g3.nbuf = h->gs3_nbuf;
         g3.k1_max = h->gs3_k1max;
@@ -647,7 +650,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         g3.pretouch = h->gs3_pretouch;
         void* args3[] = {&g3};
         CK(cudaLaunchCooperativeKernel(h->gs3_fn, dim3(h->gs3_grid), dim3(h->gs3_RP), args3, h->gs3_smem, h->stream));
-    } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
+    } else if (order == SRCFD_ORDER_GS_LEX && h->gs_impl == 2) {
         const Gs2Plan& P = h->plan2[op];
         Gs2Args ga;
         ga.s = a; ga.s.nbands = P.nbands; ga.s.band_rows = P.band_rows;
@@ -658,17 +661,17 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
         ga.pr[1] = Gs2Prob{1, 1, h->scratch2, h->partials2, h->prog2, h->halo2, h->sweeps2};   // pair: k = slot = 0 above, 1 here
         void* args2[] = {&ga};
         CK(cudaLaunchCooperativeKernel(pick_gs2(op), dim3(h->grid_gs2[op]), dim3(P.nthreads), args2, P.smem, h->stream));
-    } else if (h->p.sweep_order == SRCFD_ORDER_GS_LEX) {
+    } else if (order == SRCFD_ORDER_GS_LEX) {
         CK(cudaLaunchCooperativeKernel(pick_gs(op), dim3(h->grid_gs[op]), dim3(h->wf_threads), args, h->wf_smem, h->stream));
-    } else if (h->p.sweep_order == SRCFD_ORDER_JACOBI && op == OP_PRESSURE && h->jtb_H) {
+    } else if (order == SRCFD_ORDER_JACOBI && op == OP_PRESSURE && h->jtb_H) {
         JtbArgs ja;
         ja.s = a; ja.partials = h->jtb_partials;
         void* argsj[] = {&ja};
         CK(cudaLaunchCooperativeKernel(h->jtb_fn, dim3(h->jtb_grid), dim3(JTB_THREADS), argsj, h->jtb_smem, h->stream));
     } else {
-        if (h->p.sweep_order == SRCFD_ORDER_RED_BLACK && op == OP_QUICK)
+        if (order == SRCFD_ORDER_RED_BLACK && op == OP_QUICK)
             return fail(SRCFD_ERR_ARG, "red-black order is undefined for QUICK");
-        CK(cudaLaunchCooperativeKernel(pick_sync(op, h->p.sweep_order), dim3(h->grid_sync), dim3(SYNC_THREADS), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel(pick_sync(op, order), dim3(h->grid_sync), dim3(SYNC_THREADS), args, 0, h->stream));
     }
     h->launches += 1;
     if (h->timing) if (int rc = ev_end(h, ev)) return rc;

@@ -12,9 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRCFD_LIB") or os.path.join(_HERE, "_lib", "libsrcfd.so")
 
 SCHEME_UPWIND, SCHEME_QUICK = 0, 1
-ORDER_GS_LEX, ORDER_JACOBI, ORDER_RED_BLACK = 0, 1, 2
+ORDER_GS_LEX, ORDER_JACOBI, ORDER_RED_BLACK, ORDER_RB_JACOBI = 0, 1, 2, 3
 ORDERS = {"GS_LEX": ORDER_GS_LEX, "REFERENCE": ORDER_GS_LEX, "JACOBI": ORDER_JACOBI, "RED_BLACK": ORDER_RED_BLACK,
-          "RB": ORDER_RED_BLACK}
+          "RB": ORDER_RED_BLACK, "RB_JACOBI": ORDER_RB_JACOBI, "RB_SOR": ORDER_RB_JACOBI}
 OK, ERR_ARG, ERR_CUDA, ERR_NAN, ERR_DEADLOCK = 0, 1, 2, 3, 4
 
 

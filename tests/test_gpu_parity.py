@@ -480,3 +480,23 @@ def test_red_black_sor_pressure_bit_exact_and_faster_to_tolerance():
     finally:
         O.set_sor_omega(1.0)
     assert counts[1.85] * 5 < counts[1.0] and counts[1.5] < counts[1.0]
+
+
+@pytest.mark.parametrize("omega", [1.0, 1.5])
+def test_rb_jacobi_order_composed_solver_vs_oracle(omega):
+    """sweep_order = RB_JACOBI (north_star's "Jacobi / red-black-SOR sweeps"): Jacobi momentum (QUICK allowed), red-black
+    pressure with the SOR factor -- whole outer iterations bit-equal to the oracle's restatement of that combination."""
+    from srcfd import ldc
+    nx, ny, its = 40, 36, 12
+    st = ldc.SolverSettings(dt=1e-3, scheme='QUICK', max_iterations=its, sweep_order="RB_JACOBI", sor_omega=omega)
+    s = ldc.CFDSolver(ldc.MeshParameters(nx=nx, ny=ny), ldc.FluidProperties(Re=100.0), st, ldc.BoundaryConditions())
+    n, _ = s.solve("x", verbose=False, save=False)
+    try:
+        O.set_sor_omega(omega)
+        o = O.OracleSolver(O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme="QUICK", order=O.ORDER_RB_JACOBI))
+        m, _, _ = o.solve(its)
+    finally:
+        O.set_sor_omega(1.0)
+    assert n == m == its
+    assert list(s.total_sweeps) == o.total_sweeps.tolist()
+    assert np.array_equal(s.Var, o.Var) and np.array_equal(s.Ff, o.Ff)
