@@ -314,6 +314,9 @@ __global__ void k_jacobi_tb_commit(SolveArgs a) {
 #ifndef JTB2_T
 #define JTB2_T 256
 #endif
+#ifndef JTB2_PF
+#define JTB2_PF 0
+#endif
 constexpr int JTB2_THREADS = JTB2_T, JTB2_WARPS = JTB2_THREADS / 32;
 
 // Second try for a pair of cells whose fast division missed its range test: zero numerators (fields at rest) are exact
@@ -355,6 +358,12 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
     const double curA = nA[PH], curB = nB[PH];
     nA[PH] = L.inA ? __ldcg(pA + 3 * pitch) : 0.0;                    // row i+3 of the plane
     nB[PH] = L.inB ? __ldcg(pA + 3 * pitch + 1) : 0.0;
+#if JTB2_PF > 0
+    if (L.inA) {                                                      // rows further ahead: into L2 only (no registers held)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pA + (3 + JTB2_PF) * pitch));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qA + (1 + JTB2_PF) * pitch));
+    }
+#endif
     // right-hand side: rqX[t] = row i-1-t.  Row i is requested now and first used (as rqX[0]) one step from now.
 #pragma unroll
     for (int t = NL - 1; t > 0; --t) { rqA[t] = rqA[t - 1]; rqB[t] = rqB[t - 1]; }
@@ -363,6 +372,12 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
     rqB[NL] = L.inB ? __ldg(qA + 1) : 0.0;
     pA += pitch; qA += pitch;
     wA[0][NEW] = curA; wB[0][NEW] = curB;
+    // All NL levels are computed without a branch between them (level t+1 needs level t only as its "row below", so most
+    // of its arithmetic overlaps level t); a division that missed its range test is noticed ONCE, at the end of the step,
+    // and the step is then redone level by level with the zero-safe / IEEE path -- every input of the redo is intact:
+    // level 0 holds loaded rows, and each level's slot NEW is rewritten before the next level reads it.
+    bool bad = false;
+    double ss[NL];
 #pragma unroll
     for (int t = 1; t <= NL; ++t) {
         const int r = i - t;
@@ -371,21 +386,13 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
         const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);
         double RA, RB_;
         bool failA = false, failB = false;
-        double xA = pressure_cell3p(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, lft, rqA[t - 1], volp, D, RA, failA);
-        double xB = pressure_cell3p(cB, wB[t - 1][NEW], wB[t - 1][UP], rgt, cA, rqB[t - 1], volp, D, RB_, failB);
+        const double xA = pressure_cell3p(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, lft, rqA[t - 1], volp, D, RA, failA);
+        const double xB = pressure_cell3p(cB, wB[t - 1][NEW], wB[t - 1][UP], rgt, cA, rqB[t - 1], volp, D, RB_, failB);
         // a miss only matters in an interior column (the out-of-plane lanes of an edge strip hold zeros and always miss)
         // and once the level is fed by streamed rows (the first 2t steps of a chunk compute lead-in garbage)
-        if (__builtin_expect(((failA && L.intA) || (failB && L.intB)) && i - i_valid >= 2 * t, 0)) {
-            const Jtb2Pair o = jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, wB[t - 1][NEW], wB[t - 1][UP], lft, rgt,
-                                               rqA[t - 1], rqB[t - 1], volp, D);
-            xA = o.xA; RA = o.RA; xB = o.xB; RB_ = o.RB;
-            if (retries && (threadIdx.x & 31) == 0) atomicAdd(retries, 1ull);   // the host steers by this count (see l_jtb2_pass)
-        }
+        bad = bad || (((failA && L.intA) || (failB && L.intB)) && i - i_valid >= 2 * t);
         const double nvA = L.intA ? xA : cA, nvB = L.intB ? xB : cB;
-        if ((unsigned)(r - sr0) <= (unsigned)(sr1 - sr0)) {          // warp-uniform (sr1 < sr0 wraps to "never")
-            acc[t - 1] += RA * RA;                                    // per-lane sums, unmasked: a lane either owns both of its
-            acc[t - 1] += RB_ * RB_;                                  // columns or neither (else the unit takes the generic steps)
-        }
+        ss[t - 1] = RA * RA + RB_ * RB_;                              // a lane owns both of its columns or neither
         if (t < NL) {
             wA[t][NEW] = nvA; wB[t][NEW] = nvB;
         } else if ((unsigned)(r - ra) <= (unsigned)(rb - ra)) {
@@ -393,6 +400,29 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
             if (L.ownB) oA[1] = nvB;
         }
     }
+    if (__builtin_expect(__any_sync(0xffffffffu, bad), 0)) {
+        if (retries && (threadIdx.x & 31) == 0) atomicAdd(retries, 1ull);   // the host steers by this count (see slab_api.inl)
+#pragma unroll
+        for (int t = 1; t <= NL; ++t) {
+            const int r = i - t;
+            const double cA = wA[t - 1][CEN], cB = wB[t - 1][CEN];
+            const double lft = __shfl_up_sync(0xffffffffu, cB, 1);
+            const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);
+            const Jtb2Pair o = jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, wB[t - 1][NEW], wB[t - 1][UP], lft, rgt,
+                                               rqA[t - 1], rqB[t - 1], volp, D);
+            const double nvA = L.intA ? o.xA : cA, nvB = L.intB ? o.xB : cB;
+            ss[t - 1] = o.RA * o.RA + o.RB * o.RB;
+            if (t < NL) {
+                wA[t][NEW] = nvA; wB[t][NEW] = nvB;
+            } else if ((unsigned)(r - ra) <= (unsigned)(rb - ra)) {
+                if (L.ownA) oA[0] = nvA;
+                if (L.ownB) oA[1] = nvB;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 1; t <= NL; ++t)
+        if ((unsigned)(i - t - sr0) <= (unsigned)(sr1 - sr0)) acc[t - 1] += ss[t - 1];     // warp-uniform row test
     oA += pitch;
 }
 
