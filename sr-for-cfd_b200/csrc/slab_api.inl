@@ -23,7 +23,8 @@ struct SlabState {
     double* sweep_partials = nullptr;
     unsigned* tickets = nullptr;  // [0] push, [1] momentum sweep
     unsigned long long seq = 0;
-    int guess[3] = {8, 8, 0};
+    int guess[3] = {8, 8, 0};     // sweep counts of the last inner solves (u, v, p) and of the ones before: the prediction
+    int guess_prev[3] = {0, 0, 0};
     int block_cap = 0;            // SRCFD_SLAB_BLOCK: cap on the sweeps per block (0 = as many as the halo allows)
     int64_t exchanges = 0;
     int64_t halo_bytes = 0;       // bytes this rank pushed to neighbours
@@ -263,15 +264,28 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
     struct Rec { int S, E, nsw, n0; };
     std::vector<Rec> recs;
     int cur = 0, n = 0, b = 0;
-    // Speculation: the first round runs exactly the previous outer iteration's count (its last block ends on that sweep,
-    // so an unchanged count needs no replay); if the tolerance is still unmet, follow-up rounds grow from one pass.
-    int want = std::min(max_iter, S0->guess[slot] > 0 ? S0->guess[slot] : max_iter);
-    int grow = op == OP_PRESSURE ? 4 : 2;
+    // Speculation.  The sweep count of an inner solve drifts slowly from one outer iteration to the next, so it is predicted
+    // from the last two counts; full-size blocks run up to a little before the prediction, then SMALL blocks (one pass / two
+    // momentum sweeps) up to a little past it: the block that meets the tolerance is then short, so its replay is at most a
+    // few sweeps, and a count that grew is still covered without a host round trip (launches queued behind the hit are
+    // no-ops).  Only a badly wrong prediction costs a second round, whose blocks double in size.
+    const int last = S0->guess[slot], prev = S0->guess_prev[slot];
+    int pred = last > 0 ? last : max_iter;
+    if (last > 0 && prev > 0) pred = std::max(std::max(1, last / 2), std::min(2 * last, last + (last - prev)));
+    pred = std::min(pred, max_iter);
+    const int unit = std::min(SB, op == OP_PRESSURE ? 4 : 2);
+    const int lo = op == OP_PRESSURE ? 8 : 0, hi = op == OP_PRESSURE ? 16 : 4;
+    const bool at_cap = last <= 0 || last >= max_iter;        // the solve ran into the cap last time: whole blocks to the end
+    int want = at_cap ? max_iter : std::min(max_iter, pred + hi);
+    int fine = unit;
     int n_final = 0, final_buf = 0;
     double rms_final = 0.0;
     for (;;) {
         while (n < want) {
-            const int nsw = std::min(SB, want - n);
+            int nsw;
+            if (at_cap) nsw = std::min(SB, max_iter - n);
+            else if (n < pred - lo) nsw = std::min(SB, pred - lo - n);
+            else nsw = std::min(std::min(fine, SB), max_iter - n);
             int E = cur;
             for (int i = 0; i < G.n; ++i) TRY(slab_run_block(G[i], op, k, cur, nsw, E));
             const SlabPlanes pl = {k, E, 0, 0, 1};
@@ -296,8 +310,8 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
             break;
         }
         if (n >= max_iter || h0->ctrl_host->stop) { n_final = n; final_buf = cur; rms_final = c.rms; break; }
-        want = std::min(max_iter, n + grow);
-        grow *= 2;
+        fine = std::min(SB, fine * 2);                       // the prediction was short: larger steps from here on
+        want = std::min(max_iter, n + std::max(4 * fine, n / 4));
     }
     TRY(slab_begin(G));                                      // done = 0 again: the refresh below must run
     for (int i = 0; i < G.n; ++i) {
@@ -313,6 +327,7 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
             CK(cudaMemcpyAsync(slab_buf(h, k, 0), slab_buf(h, k, final_buf), sizeof(double) * (size_t)h->K.plane, cudaMemcpyDeviceToDevice, h->stream));
         k_slab_finish_inner<<<1, 1, 0, h->stream>>>(h->ctrl, slot, n_final, rms_final);
         LAUNCH_CHECK(h);
+        h->slab->guess_prev[slot] = h->slab->guess[slot];
         h->slab->guess[slot] = n_final;
     }
     const SlabPlanes pl = {k, 0, 0, 0, 1};
