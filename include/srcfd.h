@@ -192,6 +192,8 @@ typedef struct srcfd_coarse_result {
     int32_t reserved_;
 } srcfd_coarse_result;
 int srcfd_coarse_smem_bytes(int nx, int ny, uint64_t *bytes);
+/* *fits = 1 when srcfd_coarse_solve_batch accepts an nx x ny grid on this device (its own size gate as a query). */
+int srcfd_coarse_fits(int nx, int ny, int device, int *fits);
 int srcfd_coarse_solve_batch(const srcfd_params *params, int n_cases, int64_t max_iterations, const double *crit,
                              int resume, double *Var, double *VarOld, double *Ff, srcfd_coarse_result *results,
                              double *hist, int64_t hist_cap, double *ms);

@@ -1044,6 +1044,25 @@ extern "C" int srcfd_coarse_smem_bytes(int nx, int ny, uint64_t* bytes) {
     return SRCFD_OK;
 }
 
+// The size gate of srcfd_coarse_solve_batch as a query (same tests, same device attributes), so that callers need not copy it.
+extern "C" int srcfd_coarse_fits(int nx, int ny, int device, int* fits) {
+    if (!fits) return fail(SRCFD_ERR_ARG, "null fits");
+    *fits = 0;
+    uint64_t smem = 0;
+    if (int rc = srcfd_coarse_smem_bytes(nx, ny, &smem)) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SRCFD_ERR_CUDA, "no CUDA device: libsrcfd has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SRCFD_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(device));
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, (const void*)k_coarse_solve));
+    const int M2 = (ny + 1) / 2, threads = ((nx * M2 + 31) / 32) * 32 + 32;
+    *fits = (smem + 2048 <= (uint64_t)optin && threads <= fa.maxThreadsPerBlock) ? 1 : 0;
+    return SRCFD_OK;
+}
+
 extern "C" int srcfd_coarse_solve_batch(const srcfd_params* params, int n_cases, int64_t max_iterations, const double* crit,
                                         int resume, double* Var, double* VarOld, double* Ff, srcfd_coarse_result* results,
                                         double* hist, int64_t hist_cap, double* ms) {

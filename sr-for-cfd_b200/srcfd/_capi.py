@@ -68,7 +68,7 @@ SYMBOLS = [
     "srcfd_k_apply_bc_configured", "srcfd_k_apply_bfs_inlet",
     "srcfd_k_linear_interpolation", "srcfd_k_update_flux", "srcfd_k_under_relax", "srcfd_k_correct_velocity",
     "srcfd_k_solve_pressure", "srcfd_jacobi_pass_max", "srcfd_k_jacobi_pass", "srcfd_k_jacobi_commit", "srcfd_jacobi_sums_ptr", "srcfd_k_jacobi_snapshot", "srcfd_k_solve_momentum", "srcfd_k_implicit_solve", "srcfd_launch_count",
-    "srcfd_coarse_smem_bytes", "srcfd_coarse_solve_batch",
+    "srcfd_coarse_smem_bytes", "srcfd_coarse_fits", "srcfd_coarse_solve_batch",
     "srcfd_slab_configure", "srcfd_slab_export", "srcfd_slab_attach_ipc", "srcfd_slab_attach_local", "srcfd_slab_info", "srcfd_slab_kernel_stats",
     "srcfd_slab_exchange", "srcfd_slab_solve_pressure", "srcfd_slab_solve_momentum", "srcfd_slab_step",
     "srcfd_timing_enable", "srcfd_timing_read", "srcfd_timer_start", "srcfd_timer_stop",
@@ -310,6 +310,16 @@ def coarse_smem_bytes(nx: int, ny: int) -> int:
     n = C.c_uint64(0)
     check(lib().srcfd_coarse_smem_bytes(int(nx), int(ny), C.byref(n)))
     return n.value
+
+
+def coarse_fits(nx: int, ny: int, device: int = 0):
+    """The library's own size gate of the one-CTA solver on `device`; None when no CUDA device is present."""
+    f = C.c_int(0)
+    rc = lib().srcfd_coarse_fits(int(nx), int(ny), int(device), C.byref(f))
+    if rc == ERR_CUDA:
+        return None
+    check(rc)
+    return bool(f.value)
 
 
 def coarse_solve_batch(params, max_iterations: int, crit, hist_cap: int = 0, state=None):

@@ -149,8 +149,13 @@ _ONE_CTA_SMEM = 227 * 1024 - 2048      # opt-in shared memory per CTA on sm_100a
 _ONE_CTA_THREADS = 640                # register-limited block size of k_coarse_solve
 
 
-def fits_one_cta(nx: int, ny: int) -> bool:
-    """True when srcfd_coarse_solve_batch accepts the grid (state in shared memory, one thread per 2 cells of a row)."""
+def fits_one_cta(nx: int, ny: int, device: int = 0) -> bool:
+    """True when srcfd_coarse_solve_batch accepts the grid (state in shared memory, one thread per 2 cells of a row).
+    The library answers from the device's and the kernel's own attributes (srcfd_coarse_fits); the constants above
+    only serve where no CUDA device is present (documentation, CPU tests)."""
+    ans = capi.coarse_fits(nx, ny, device)
+    if ans is not None:
+        return ans
     threads = ((nx * ((ny + 1) // 2) + 31) // 32) * 32 + 32
     return threads <= _ONE_CTA_THREADS and capi.coarse_smem_bytes(nx, ny) <= _ONE_CTA_SMEM
 
@@ -313,7 +318,7 @@ class CFDSolver:
         order = getattr(self.settings, 'sweep_order', 'GS_LEX')
         if not self.resident_solve or (order.upper() if isinstance(order, str) else order) not in ('GS_LEX', capi.ORDERS['GS_LEX']):
             return False
-        return fits_one_cta(self.mesh.nx, self.mesh.ny)
+        return fits_one_cta(self.mesh.nx, self.mesh.ny, getattr(self, 'device', 0))
 
     def _solve_resident(self, crit, max_it, verbose) -> int:
         """solve() through srcfd_coarse_solve_batch (one case): same iterates, same history cadence; the
