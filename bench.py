@@ -520,23 +520,28 @@ def decoder_record(device, torch):
     z = torch.randn(B, 50, device=f"cuda:{device}", dtype=torch.float32, generator=torch.Generator(f"cuda:{device}").manual_seed(0))
     o = torch.empty(B, 400, 400, 1, device=f"cuda:{device}", dtype=torch.float32)
     res = {}
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32", "bf16x3", "bf16"):
         sr.set_precision(mode)
         for _ in range(2):
             sr.decode_device(dec, z.data_ptr(), 64, o.data_ptr())
         ms = min(sr.decode_device(dec, z.data_ptr(), B, o.data_ptr()) for _ in range(3))
         res[mode] = {"ms": ms, "samples_per_s": B / (ms * 1e-3), "tflops": B * DEC_FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12,
                      "output_write_gbs": B * 640000 / (ms * 1e-3) / 1e9}
-    sr.set_precision("fp32")
+    sr.set_precision("bf16x3")
     torch.cuda.synchronize()
+    tf = res["bf16x3"]["tflops"]
     return {"metric": "SR decoder inference throughput", "batch": B, "unit": "samples/s",
-            "value": res["fp32"]["samples_per_s"], "value_path": "fp32 CUDA cores (the path that meets 1e-4 against the restatement)",
+            "value": res["bf16x3"]["samples_per_s"],
+            "value_path": "bf16x3: every ConvT on tcgen05 as three bf16 MMAs per K-step (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi), fp32 activations, "
+                          "epilogues and final conv -- the library's default; held to the fp32 path's tolerance (rtol 1e-4 / atol 5e-5 "
+                          "against the numpy restatement, tests/test_gpu_sr.py)",
             "paths": res, "tc_error": bool(sr.tc_error()),
-            "bf16_note": "bf16 operands / f32 accumulate on tcgen05: within 3e-2 of the output range of the fp32 restatement -- "
-                         "narrower arithmetic than the reference's fp32, reported beside the fp32 path, not as the value",
+            "bf16_note": "bf16 operands AND activations on tcgen05: within 3e-2 of the output range of the fp32 restatement -- narrower "
+                         "arithmetic than the reference's fp32, reported beside the value, not as the value",
             "parity": "unpinned (no decoder weights / TensorFlow / input-output pair in the reference tree): synthetic seed-0 weights",
-            "roofline": {"bound": "tensor", "achieved": res["bf16"]["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": res["bf16"]["tflops"] / tf_peak, "hbm_output_frac": res["bf16"]["output_write_gbs"] / hbm}}
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
+                         "note": "useful FLOPs (276 MFLOP per sample) / time; the split path issues 3x the MMAs",
+                         "hbm_output_frac": res["bf16x3"]["output_write_gbs"] / hbm}}
 
 
 def run_ours(args):

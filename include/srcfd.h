@@ -238,7 +238,11 @@ int srcfd_sr_predict(srcfd_sr *h, const float *x /* (B,10,10,1) */, int B, float
 int srcfd_sr_super_resolve(srcfd_sr *h, const float *x, int B, const double *stats, int adaptive, double blend, float *out);
 /* decoder on device-resident latents/outputs (cudaMalloc'ed by the caller); *ms = CUDA-event time of the batch */
 int srcfd_sr_decode_device(srcfd_sr *h, uint64_t z_dev, int B, uint64_t out_dev, double *ms);
-/* 0 = fp32 CUDA cores (default; the parity path), 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers */
+/* 0 = fp32 CUDA cores, 1 = bf16 tcgen05 tensor cores for the ConvT layers and the final conv (bf16 activations),
+ * 2 = as 1 with the final conv on the CUDA-core tile kernel (what the tensor-core final conv is tested against),
+ * 3 = split-operand tensor cores: fp32 activations, every product as three bf16 MMAs (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi),
+ *     fp32 epilogues and final conv -- the accuracy of the fp32 path (1e-4 against the restatement) at tensor-core speed;
+ *     THE DEFAULT of a new srcfd_sr context */
 int srcfd_sr_set_precision(srcfd_sr *h, int mode);
 int srcfd_sr_tc_error(srcfd_sr *h, int *flag);
 /* one tensor-core ConvT layer (1..4) in isolation, host fp32 in/out (operands rounded to bf16): parity tests */

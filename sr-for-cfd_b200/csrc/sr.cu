@@ -46,6 +46,32 @@ __global__ void k_dense(const float* __restrict__ in, const float* __restrict__ 
     st_act<TOUT>(out + t, act ? swishf(acc) : acc);
 }
 
+// Same layer for small K (the decoder's Dense 50 -> 36 864): a thread keeps one output column for BT samples, so a weight
+// is fetched once per BT samples instead of once per sample (the one-output-per-thread form re-reads the 7.4 MB matrix
+// from L2 for every sample: 76 us per 128 samples, L2-bound).  Per output the k-ascending fma order is unchanged.
+template <typename TOUT, int BT>
+__global__ void __launch_bounds__(256) k_dense_bt(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                                                   TOUT* __restrict__ out, int B, int K, int N, int act) {
+    __shared__ float xs[BT * 128];                             // K <= 128
+    const int b0 = blockIdx.y * BT, nb = min(BT, B - b0);
+    for (int c = threadIdx.x; c < BT * K; c += blockDim.x) { const int j = c / K; xs[c] = j < nb ? in[(long long)(b0 + j) * K + (c - j * K)] : 0.f; }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) acc[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float w = W[(long long)k * N + n];
+#pragma unroll
+        for (int j = 0; j < BT; ++j) acc[j] = fmaf(xs[j * K + k], w, acc[j]);
+    }
+    const float bn = bias[n];
+#pragma unroll
+    for (int j = 0; j < BT; ++j)
+        if (j < nb) { const float v = acc[j] + bn; st_act<TOUT>(out + (long long)(b0 + j) * N + n, act ? swishf(v) : v); }
+}
+
 // Conv2D, cross-correlation, zero padding (pt, pl) at the top/left; W (kh, kw, Cin, Cout)
 template <typename TIN>
 __device__ __forceinline__ float ld_act(const TIN* p) { return (float)*p; }
@@ -215,7 +241,7 @@ __global__ void k_sr_post(float* __restrict__ y, const double* __restrict__ stat
     }
 }
 
-struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; };
+struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; __nv_bfloat16* Wlo = nullptr; };   // Wlo = bf16(W - Wbf): split-operand path
 
 }  // namespace
 
@@ -229,10 +255,15 @@ struct srcfd_sr {
     int chunk = 0;
     cudaEvent_t ea = nullptr, eb = nullptr;
     int64_t launches = 0;
-    int precision = 0;                 // 0: fp32 CUDA cores everywhere; 1: bf16 tcgen05 for the four 2x2/stride-2 ConvT layers
+    int precision = 3;                 // 3 (default): split-operand tcgen05 (fp32-grade accuracy); 0: fp32 CUDA cores; 1: bf16 tcgen05 (fastest, bf16 activations)
     __nv_bfloat16* actbf[6] = {nullptr};   // bf16 activations of layers 1..5 (index = layer) for one chunk
     int* tc_err = nullptr;
     FinalConvW fcw;                    // host copy of the last layer's 72 weights + bias (kernel argument)
+    // environment knobs, read once at creation
+    int tc_persist = 16;               // SRCFD_TC_PERSIST: CTAs per SM of the persistent ConvT launch (batch 1024: 8.37 ms with one
+                                       // tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM)
+    int final_tc = 1;                  // SRCFD_FINAL_TC=0: final conv on the CUDA-core tile kernel
+    int final_tc_rows = 8;             // SRCFD_FINAL_TC_ROWS: 4 | 8 | 16 output rows per CTA of the tensor-core final conv
     double* stats_dev = nullptr;       // per-field {mean_lr, std_lr, mean_hr, std_hr} of srcfd_sr_super_resolve
     int stats_cap = 0;
 };
@@ -282,7 +313,6 @@ int run_encoder(srcfd_sr* h, const float* x_dev, int B, float* z_dev) {
     SRCK(cudaGetLastError());
     return SRCFD_OK;
 }
-constexpr int TC_PERSIST_DEFAULT = 16;      // batch 1024: 8.37 ms with one tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM
 template <int KD, int ND>
 int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* Wbf, const float* bias, __nv_bfloat16* out,
                     int B, int H) {
@@ -295,14 +325,31 @@ int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* W
     static int sms_dev[64] = {0};
     if (!sms_dev[h->dev & 63]) SRCK(cudaDeviceGetAttribute(&sms_dev[h->dev & 63], cudaDevAttrMultiProcessorCount, h->dev));
     const long long ntiles = (M + 127) / 128;
-    const char* pe = getenv("SRCFD_TC_PERSIST");
-    const int per_sm = std::min(pe ? atoi(pe) : TC_PERSIST_DEFAULT, 512 / (ND < 32 ? 32 : ND));
+    const int per_sm = std::min(h->tc_persist, 512 / (ND < 32 ? 32 : ND));
     const unsigned grid = per_sm > 0 ? (unsigned)std::min<long long>(ntiles, (long long)per_sm * sms_dev[h->dev & 63]) : (unsigned)ntiles;
     srtc::k_convT2x2_tc<KD, ND><<<grid, 128, smem, h->stream>>>(in, Wbf, bias, out, M, H, H, h->tc_err);
     h->launches += 1;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
 }
+// split-operand (bf16 x 3) ConvT layer: fp32 activation in and out
+template <int KD, int ND>
+int launch_convT_tc3(srcfd_sr* h, const float* in, const Layer& L, float* out, int B, int H) {
+    const long long M = (long long)B * H * H;
+    const size_t smem = srtc::convT_tc3_smem<KD, ND, 1>();
+    static bool attr_done[64] = {false};
+    if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<KD, ND, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
+    static int sms_dev[64] = {0};
+    if (!sms_dev[h->dev & 63]) SRCK(cudaDeviceGetAttribute(&sms_dev[h->dev & 63], cudaDevAttrMultiProcessorCount, h->dev));
+    const long long ntiles = (M + 127) / 128;
+    const int per_sm = std::max(1, std::min(std::min(h->tc_persist, 512 / (ND < 32 ? 32 : ND)), (int)((size_t)220 * 1024 / smem)));
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)per_sm * sms_dev[h->dev & 63]);
+    srtc::k_convT2x2_tc3<KD, ND, 0, 1><<<grid, 128, smem, h->stream>>>(in, L.Wbf, L.Wlo, L.b, out, M, H, H, h->tc_err);
+    h->launches += 1;
+    SRCK(cudaGetLastError());
+    return SRCFD_OK;
+}
+
 // tensor-core ConvT layer l (1..4): input H = 25 * 2^(l-1), Cin = 128 >> (l-1)
 int run_convT_tc(srcfd_sr* h, int l, const __nv_bfloat16* in, __nv_bfloat16* out, int B) {
     switch (l) {
@@ -316,10 +363,11 @@ int run_convT_tc(srcfd_sr* h, int l, const __nv_bfloat16* in, __nv_bfloat16* out
 
 // decoder on `B` samples: z_dev (B,50) -> out_dev (B,400,400,1)
 int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
-    if (h->precision == 0)
-        k_dense<float><<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
-    else
-        k_dense<__nv_bfloat16><<<nblk((long long)B * 36864), 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->actbf[0], B, 50, 36864, 1);
+    {
+        const dim3 gd(36864 / 256, (B + 7) / 8);
+        if (h->precision == 0 || h->precision == 3) k_dense_bt<float, 8><<<gd, 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->act[0], B, 50, 36864, 1);
+        else k_dense_bt<__nv_bfloat16, 8><<<gd, 256, 0, h->stream>>>(z_dev, h->dec[0].W, h->dec[0].b, h->actbf[0], B, 50, 36864, 1);
+    }
     const int hw[6] = {12, 25, 50, 100, 200, 400}, ch[6] = {256, 128, 64, 32, 16, 8};
     h->launches += 1;
     if (h->precision == 0) {
@@ -330,6 +378,24 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         }
         k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->fcw, out_dev, B, 400, 400);
         h->launches += 6;
+    } else if (h->precision == 3) {
+        // split-operand tensor-core path: fp32 activations end to end, every ConvT on tcgen05 as three bf16 MMAs per K-step
+        {
+            const long long M = (long long)B * 144;
+            const size_t smem = srtc::convT_tc3_smem<256, 128, 2>();
+            static bool attr_done[64] = {false};
+            if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<256, 128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
+            srtc::k_convT2x2_tc3<256, 128, 1, 2><<<dim3((unsigned)((M + 127) / 128), 9), 128, smem, h->stream>>>(
+                h->act[0], h->dec[1].Wbf, h->dec[1].Wlo, h->dec[1].b, nullptr, M, 12, 12, h->tc_err, h->act[5], 1152);
+            srtc::k_col2im_3x3s2_f32<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->act[1], B);
+            h->launches += 2;
+        }
+        if (int rc = launch_convT_tc3<128, 256>(h, h->act[1], h->dec[2], h->act[2], B, 25)) return rc;
+        if (int rc = launch_convT_tc3<64, 128>(h, h->act[2], h->dec[3], h->act[3], B, 50)) return rc;
+        if (int rc = launch_convT_tc3<32, 64>(h, h->act[3], h->dec[4], h->act[4], B, 100)) return rc;
+        if (int rc = launch_convT_tc3<16, 32>(h, h->act[4], h->dec[5], h->act[5], B, 200)) return rc;
+        k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->fcw, out_dev, B, 400, 400);
+        h->launches += 1;
     } else {
         // ConvT1 (3x3, stride 2: overlapping taps): tensor-core GEMM per tap into Y (act[5] reused as fp32 scratch,
         // B*144 x 1152), then col2im + bias + swish -> bf16 activation
@@ -345,11 +411,10 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         h->launches += 2;
         for (int l = 1; l <= 4; ++l)
             if (int rc = run_convT_tc(h, l, h->actbf[l], h->actbf[l + 1], B)) return rc;
-        const char* ftc = getenv("SRCFD_FINAL_TC");                 // 0: the CUDA-core tile kernel (read per call: tests toggle it)
-        if (!(ftc && atoi(ftc) == 0)) {
+        if (h->final_tc) {
             srtc::FinalW fw;
             memcpy(fw.w, h->fcw.w, sizeof(fw.w)); fw.b = h->fcw.b;
-            const int R = getenv("SRCFD_FINAL_TC_ROWS") ? atoi(getenv("SRCFD_FINAL_TC_ROWS")) : 8;
+            const int R = h->final_tc_rows;
             const dim3 grid((400 + 127) / 128, (400 + R - 1) / R, B);
             if (R == 4) srtc::k_conv3x3_c8_final_tc<4><<<grid, 128, srtc::ft_smem<4>(), h->stream>>>(h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
             else if (R == 16) srtc::k_conv3x3_c8_final_tc<16><<<grid, 128, srtc::ft_smem<16>(), h->stream>>>(h->actbf[5], fw, out_dev, 400, 400, h->tc_err);
@@ -380,6 +445,9 @@ int srcfd_sr_create(int device, srcfd_sr** out) {
     SRCK(cudaSetDevice(device));
     SRCK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     SRCK(cudaEventCreate(&h->ea)); SRCK(cudaEventCreate(&h->eb));
+    if (const char* e = getenv("SRCFD_TC_PERSIST")) h->tc_persist = atoi(e);
+    if (const char* e = getenv("SRCFD_FINAL_TC")) h->final_tc = atoi(e);
+    if (const char* e = getenv("SRCFD_FINAL_TC_ROWS")) h->final_tc_rows = atoi(e);
     *out = h;
     return SRCFD_OK;
 }
@@ -389,7 +457,7 @@ int srcfd_sr_destroy(srcfd_sr* h) {
     cudaSetDevice(h->dev);
     cudaStreamSynchronize(h->stream);
     for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
-    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); }
+    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); cudaFree(l.Wlo); }
     for (int i = 0; i < 6; ++i) cudaFree(h->actbf[i]);
     cudaFree(h->tc_err); cudaFree(h->stats_dev);
     for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
@@ -429,10 +497,15 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
         if (int rc = upload(&h->dec[l + 1].b, biases[l + 1], cout[l], h->stream)) return rc;
         {                 // tensor-core operand: the Keras layout (ky,kx,co | ci) is already the K-major (N, K) matrix
             const size_t n = (size_t)taps[l] * cout[l] * cin[l];
-            std::vector<__nv_bfloat16> wb(n);
-            for (size_t i = 0; i < n; ++i) wb[i] = __float2bfloat16(kernels[l + 1][i]);
+            std::vector<__nv_bfloat16> wb(n), wl(n);
+            for (size_t i = 0; i < n; ++i) {
+                wb[i] = __float2bfloat16(kernels[l + 1][i]);
+                wl[i] = __float2bfloat16(kernels[l + 1][i] - __bfloat162float(wb[i]));      // the part the first bf16 dropped
+            }
             if (!h->dec[l + 1].Wbf) SRCK(cudaMalloc(&h->dec[l + 1].Wbf, n * sizeof(__nv_bfloat16)));
+            if (!h->dec[l + 1].Wlo) SRCK(cudaMalloc(&h->dec[l + 1].Wlo, n * sizeof(__nv_bfloat16)));
             SRCK(cudaMemcpy(h->dec[l + 1].Wbf, wb.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            SRCK(cudaMemcpy(h->dec[l + 1].Wlo, wl.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
         }
     }
     if (int rc = upload(&h->dec[6].W, kernels[6], 3 * 3 * 8 * 1, h->stream)) return rc;
@@ -539,8 +612,10 @@ int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev,
 }
 // 0 = fp32 CUDA cores (default, parity path); 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers
 int srcfd_sr_set_precision(srcfd_sr* h, int mode) {
-    if (!h || mode < 0 || mode > 1) return sr_fail(SRCFD_ERR_ARG, "bad argument");
-    h->precision = mode;
+    if (!h || mode < 0 || mode > 3) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    h->precision = mode == 0 ? 0 : mode == 3 ? 3 : 1;
+    if (mode == 1) h->final_tc = 1;        // mode 2: bf16 layers with the final conv on the CUDA-core tile kernel (parity tests)
+    if (mode == 2) h->final_tc = 0;
     return SRCFD_OK;
 }
 // 1 if a tensor-core kernel ever timed out waiting for its accumulator (diagnostic; the kernels never hang)

@@ -40,7 +40,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+// swish(x) = x * sigmoid(x) with sigmoid(x) = 0.5 + 0.5 * tanh(x / 2): one MUFU (tanh.approx.f32, relative error 2^-11) and
+// three FMA-pipe operations instead of exp + full-precision division (2 MUFU + ~10).  The result is rounded to bf16
+// (2^-8) right after, so the approximation is invisible at the output precision of this path; the fp32 path keeps expf.
+__device__ __forceinline__ float swishf(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f);
+}
 
 // A: (M, KD) bf16 row-major.  Wk: (ND, KD) bf16 row-major (ND = 4*Cout, n = (dy*2+dx)*Cout + co).  bias: (Cout) fp32.
 // out: (B, 2H, 2W, Cout) bf16.  M = B*H*W.  err: set to 1 if the MMA completion wait times out (never hang).
@@ -60,7 +67,9 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
     unsigned char* sB = smem_raw + (size_t)MT * KD * 2;        // ND x KD bf16
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[COUT];               // read as float4 broadcasts by the epilogue
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (EPI == 0) for (int c = tid; c < COUT; c += 128) s_bias[c] = bias[c];
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ND < 32 ? 32 : ND) : "memory");
@@ -147,9 +156,12 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
                 for (int g = 0; g < 16; g += 8) {
                     const int n = c0 + g, tap = n / COUT, co = n - tap * COUT;
                     const int dy = tap >> 1, dx = tap & 1;
-                    __nv_bfloat16 o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16(swishf(__uint_as_float(v[g + e]) + bias[co + e]));
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co), b1 = *reinterpret_cast<const float4*>(s_bias + co + 4);
+                    __nv_bfloat162 o[4];                         // cvt.rn.bf16x2.f32: two values per conversion
+                    o[0] = __floats2bfloat162_rn(swishf(__uint_as_float(v[g + 0]) + b0.x), swishf(__uint_as_float(v[g + 1]) + b0.y));
+                    o[1] = __floats2bfloat162_rn(swishf(__uint_as_float(v[g + 2]) + b0.z), swishf(__uint_as_float(v[g + 3]) + b0.w));
+                    o[2] = __floats2bfloat162_rn(swishf(__uint_as_float(v[g + 4]) + b1.x), swishf(__uint_as_float(v[g + 5]) + b1.y));
+                    o[3] = __floats2bfloat162_rn(swishf(__uint_as_float(v[g + 6]) + b1.z), swishf(__uint_as_float(v[g + 7]) + b1.w));
                     __nv_bfloat16* dst = out + ((((long long)b * (2 * H) + (2 * y + dy)) * OW + (2 * x + dx)) * COUT + co);
                     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
                 }
@@ -165,6 +177,180 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
 
 template <int KD, int ND>
 constexpr size_t convT_tc_smem() { return (size_t)(128 + ND) * KD * 2; }
+
+// ---- split-operand variant (round 2): fp32 accuracy from the bf16 tensor cores ---------------------------------------------
+// a = a_hi + a_lo, w = w_hi + w_lo with every part a bf16: a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (the dropped a_lo*w_lo and
+// the parts' own rounding are ~2^-16 of the product); three MMAs per K-step accumulate in the same fp32 TMEM accumulator.
+// The activations stay fp32 in HBM (same traffic as the fp32 CUDA-core path): they are split while they are staged
+// (hi = bf16(a), lo = bf16(a - hi)); the weights are split once at upload; the epilogue is fp32 (expf swish, fp32 store).
+// KPART > 1 stages the A tile in K-parts (the 3x3 layer: K = 256 would need 256 KB for both operands' two halves); the
+// weights stay resident.  Same tile / descriptor / epilogue structure as k_convT2x2_tc.
+__device__ __forceinline__ float swish_exact(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    __nv_bfloat162 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        l[e] = __floats2bfloat162_rn(v[2 * e] - __low2float(h[e]), v[2 * e + 1] - __high2float(h[e]));
+    }
+    hi = *reinterpret_cast<const uint4*>(h); lo = *reinterpret_cast<const uint4*>(l);
+}
+template <int KD, int ND, int EPI, int KPART>
+__global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Whi,
+                                                       const __nv_bfloat16* __restrict__ Wlo, const float* __restrict__ bias,
+                                                       float* __restrict__ out, long long M, int H, int Wd, int* err,
+                                                       float* __restrict__ Y = nullptr, int ldy = 0) {
+    constexpr int MT = 128, COUT = ND / 4, KP = KD / KPART, KCP = KP / 8, KC = KD / 8;
+    if (EPI == 1) { Whi += (size_t)blockIdx.y * ND * KD; Wlo += (size_t)blockIdx.y * ND * KD; }
+    constexpr uint32_t LBO_A = (MT / 8) * 128, LBO_B = (ND / 8) * 128, SBO = 128;
+    constexpr uint32_t ABYTES = MT * KP * 2, BBYTES = ND * KD * 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sAh = smem_raw;
+    unsigned char* sAl = smem_raw + ABYTES;
+    unsigned char* sBh = smem_raw + 2 * (size_t)ABYTES;
+    unsigned char* sBl = sBh + BBYTES;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[COUT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (EPI == 0) for (int c = tid; c < COUT; c += 128) s_bias[c] = bias[c];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ND < 32 ? 32 : ND) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < ND * KC; c += 128) {                   // both halves of the weights, once per CTA
+        const int n = c / KC, kc = c - n * KC;
+        const size_t so = (size_t)kc * LBO_B + (n >> 3) * SBO + (n & 7) * 16;
+        *reinterpret_cast<uint4*>(sBh + so) = *reinterpret_cast<const uint4*>(Whi + (size_t)n * KD + kc * 8);
+        *reinterpret_cast<uint4*>(sBl + so) = *reinterpret_cast<const uint4*>(Wlo + (size_t)n * KD + kc * 8);
+    }
+    const long long ntiles = (M + MT - 1) / MT;
+    uint32_t phase = 0;
+    const int OW = 2 * Wd;
+    bool dead = false;
+    for (long long tile = blockIdx.x; tile < ntiles && !dead; tile += gridDim.x) {
+        const long long m0 = tile * MT;
+#pragma unroll 1
+        for (int part = 0; part < KPART && !dead; ++part, phase ^= 1u) {
+            // ---- stage this K-part of the A tile, split into its two bf16 halves (zero rows past M)
+            for (int c = tid; c < MT * KCP; c += 128) {
+                const int r = c / KCP, kc = c - r * KCP;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (m0 + r < M) {
+                    const float4* src = reinterpret_cast<const float4*>(A + (m0 + r) * KD + part * KP + kc * 8);
+                    const float4 a = src[0], b = src[1];
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                }
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                const size_t so = (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16;
+                *reinterpret_cast<uint4*>(sAh + so) = hi;
+                *reinterpret_cast<uint4*>(sAl + so) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                     // also: every warp has drained the previous tile's accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem = tmem_base_s;
+            if (tid == 0) {
+                constexpr uint32_t idesc = make_idesc_bf16(MT, ND);
+                const uint32_t ah = smem_u32(sAh), al = smem_u32(sAl), bh = smem_u32(sBh), bl = smem_u32(sBl);
+#pragma unroll
+                for (int k = 0; k < KP / 16; ++k) {
+                    const uint32_t ao = (uint32_t)k * 2 * LBO_A, bo = (uint32_t)(part * (KP / 16) + k) * 2 * LBO_B;
+                    const uint64_t adh = make_smem_desc(ah + ao, LBO_A, SBO), adl = make_smem_desc(al + ao, LBO_A, SBO);
+                    const uint64_t bdh = make_smem_desc(bh + bo, LBO_B, SBO), bdl = make_smem_desc(bl + bo, LBO_B, SBO);
+                    umma_bf16(tmem, adh, bdh, idesc, (part > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem, adh, bdl, idesc, 1u);
+                    umma_bf16(tmem, adl, bdh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+            }
+            {                                                    // bounded wait: never hang the GPU
+                uint32_t done = 0;
+                for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                 : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+                }
+                if (!done) { if (lane == 0) atomicExch(err, 1); dead = true; }
+            }
+            dead = __syncthreads_or(dead ? 1 : 0) != 0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (dead) break;
+        // ---- epilogue: thread = accumulator row (TMEM lane) 32*warp + lane
+        const long long m = m0 + warp * 32 + lane;
+        const bool valid = m < M;
+        long long pix = valid ? m : 0;
+        const int x = (int)(pix % Wd); pix /= Wd;
+        const int y = (int)(pix % H);
+        const long long b = pix / H;
+        const uint32_t tmem = tmem_base_s;
+#pragma unroll 1
+        for (int c0 = 0; c0 < ND; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (EPI == 1) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(Y + m * ldy + (long long)blockIdx.y * ND + c0);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int g = 0; g < 16; g += 8) {
+                    const int n = c0 + g, tap = n / COUT, co = n - tap * COUT;
+                    const int dy = tap >> 1, dx = tap & 1;
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + co), b1 = *reinterpret_cast<const float4*>(s_bias + co + 4);
+                    float4* dst = reinterpret_cast<float4*>(out + ((((long long)b * (2 * H) + (2 * y + dy)) * OW + (2 * x + dx)) * COUT + co));
+                    dst[0] = make_float4(swish_exact(__uint_as_float(v[g + 0]) + b0.x), swish_exact(__uint_as_float(v[g + 1]) + b0.y),
+                                         swish_exact(__uint_as_float(v[g + 2]) + b0.z), swish_exact(__uint_as_float(v[g + 3]) + b0.w));
+                    dst[1] = make_float4(swish_exact(__uint_as_float(v[g + 4]) + b1.x), swish_exact(__uint_as_float(v[g + 5]) + b1.y),
+                                         swish_exact(__uint_as_float(v[g + 6]) + b1.z), swish_exact(__uint_as_float(v[g + 7]) + b1.w));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(ND < 32 ? 32 : ND) : "memory");
+}
+template <int KD, int ND, int KPART>
+constexpr size_t convT_tc3_smem() { return (size_t)2 * 128 * (KD / KPART) * 2 + (size_t)2 * ND * KD * 2; }
+
+// col2im of the 3x3 / stride-2 layer with an fp32 activation out (split-operand path)
+__global__ void k_col2im_3x3s2_f32(const float* __restrict__ Y, const float* __restrict__ bias, float* __restrict__ out, int B) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * 25 * 25 * 128) return;
+    const int co = (int)(t & 127);
+    long long p = t >> 7;
+    const int X = (int)(p % 25); p /= 25;
+    const int Yo = (int)(p % 25);
+    const long long b = p / 25;
+    float acc = bias[co];
+    for (int ky = Yo & 1; ky < 3; ky += 2) {
+        const int y = (Yo - ky) >> 1;
+        if (y < 0 || y >= 12) continue;
+        for (int kx = X & 1; kx < 3; kx += 2) {
+            const int x = (X - kx) >> 1;
+            if (x < 0 || x >= 12) continue;
+            acc += Y[((b * 12 + y) * 12 + x) * 1152 + (ky * 3 + kx) * 128 + co];
+        }
+    }
+    out[t] = swish_exact(acc);
+}
 
 // Conv2DTranspose(128, 3x3, stride 2, valid) from the per-tap products Y (B*144, 9*128): sum the <= 4 taps that hit
 // each output pixel, add bias, swish, write the bf16 NHWC activation (B, 25, 25, 128).

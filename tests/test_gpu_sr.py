@@ -1,5 +1,6 @@
 """CUDA SR autoencoder (through the C ABI) against the CPU restatement.  `-m gpu`.
-fp32 throughout; tolerance 1e-4 relative / 5e-5 absolute (different summation order, expf vs np.exp)."""
+fp32 results throughout (default precision: split-operand tensor cores, 'bf16x3'; the fp32 CUDA-core path is held to the
+same bar); tolerance 1e-4 relative / 5e-5 absolute (different summation order, expf vs np.exp)."""
 import os
 
 import numpy as np
@@ -83,7 +84,7 @@ def test_tensor_core_convT_layer(layer):
 
 def test_decoder_bf16_tensor_core_path():
     """Whole decoder with the tensor-core layers: bf16 operands => compare with the fp32 restatement at 3e-2 of the
-    output range (this path is the throughput option; fp32 stays the default and the parity path)."""
+    output range (the throughput option; the default is the split-operand path, held to the fp32 bar)."""
     from srcfd import sr
     dec = sr.synthetic_decoder(0)
     z = np.random.default_rng(11).standard_normal((3, 50)).astype(np.float32)
@@ -91,7 +92,7 @@ def test_decoder_bf16_tensor_core_path():
     try:
         out = dec.predict(z)
     finally:
-        sr.set_precision("fp32")
+        sr.set_precision("bf16x3")                         # back to the library's default
     assert not sr.tc_error()
     ref = S.decoder_forward(z, dec.weights)
     scale = np.abs(ref).max()
@@ -106,15 +107,13 @@ def test_final_conv_on_tensor_cores_matches_cuda_core_kernel():
     from srcfd import sr
     dec = sr.synthetic_decoder(0)
     z = np.random.default_rng(5).standard_normal((2, 50)).astype(np.float32)
-    sr.set_precision("bf16")
     try:
-        os.environ["SRCFD_FINAL_TC"] = "0"
+        sr.set_precision("bf16_cc_final")
         ref = dec.predict(z)
-        os.environ["SRCFD_FINAL_TC"] = "1"
+        sr.set_precision("bf16")
         out = dec.predict(z)
     finally:
-        os.environ.pop("SRCFD_FINAL_TC", None)
-        sr.set_precision("fp32")
+        sr.set_precision("bf16x3")                         # back to the library's default
     assert not sr.tc_error()
     assert out.shape == ref.shape == (2, 400, 400, 1)
     scale = np.abs(ref).max()
@@ -158,3 +157,26 @@ def test_super_resolve_device_pipeline(golden_dir):
                 continue
             np.testing.assert_allclose(got[b], ref, rtol=2e-4, atol=2e-4 * max(1.0, float(np.max(np.abs(ref)))))
     assert sr.launch_count() > 0
+
+
+@pytest.mark.parametrize("B", [1, 5, 130])
+def test_decoder_split_operand_tensor_cores_meet_the_fp32_bar(B):
+    """precision 'bf16x3': every ConvT on tcgen05 as three bf16 MMAs per K-step (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi) with
+    fp32 activations, epilogues and final conv -- held to the SAME tolerance as the fp32 CUDA-core path
+    (rtol 1e-4 / atol 5e-5 against the numpy restatement), and equal to that path to the same bar."""
+    from srcfd import sr
+    dec = sr.synthetic_decoder(0)
+    z = np.random.default_rng(100 + B).standard_normal((B, 50)).astype(np.float32)
+    try:
+        sr.set_precision("bf16x3")
+        out = dec.predict(z)
+        sr.set_precision("fp32")
+        ref32 = dec.predict(z)
+    finally:
+        sr.set_precision("bf16x3")                         # the library's default
+    assert not sr.tc_error()
+    nref = min(B, 2)
+    np.testing.assert_allclose(out[:nref], S.decoder_forward(z[:nref], dec.weights), rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(out, ref32, rtol=1e-4, atol=5e-5)
+    if B > 128:                                            # the second 128-sample chunk, and a partial last tile per layer
+        np.testing.assert_allclose(out[129], ref32[129], rtol=1e-4, atol=5e-5)
