@@ -185,7 +185,8 @@ constexpr size_t convT_tc_smem() { return (size_t)(128 + ND) * KD * 2; }
 // (hi = bf16(a), lo = bf16(a - hi)); the weights are split once at upload; the epilogue is fp32 (expf swish, fp32 store).
 // KPART > 1 stages the A tile in K-parts (the 3x3 layer: K = 256 would need 256 KB for both operands' two halves); the
 // weights stay resident.  Same tile / descriptor / epilogue structure as k_convT2x2_tc.
-__device__ __forceinline__ float swish_exact(float x) { return x / (1.0f + __expf(-x)); }
+// expf + approximate division (MUFU.EX2, MUFU.RCP: ~2 ulp each) -- three orders of magnitude inside the 1e-4 bar of this path
+__device__ __forceinline__ float swish_exact(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     __nv_bfloat162 h[4], l[4];
 #pragma unroll
