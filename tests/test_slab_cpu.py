@@ -140,3 +140,60 @@ def test_two_rank_slab_jacobi_matches_single_domain_oracle():
         assert np.array_equal(rows, B[2, 1:-1]), (tol, cap, np.max(np.abs(rows - B[2, 1:-1])))
         counts.append(n)
     assert counts[0] == 10 and counts[1] == 3 and 1 < counts[2] < 40 and counts[2] % 4 != 0 or counts[3] % 4 != 0
+
+
+# ---- the set-up plumbing of the product path: cudaIpc blobs handed round once over torch.distributed (gloo here) -------------
+class _FakeSlab:
+    """Stands in for GpuSlab where there is no GPU: same attributes attach_distributed touches."""
+
+    def __init__(self, world, rank):
+        self.part = SlabPartition(64, world, rank, 8)
+        self.attached = {}
+
+    def export_blob(self):
+        return bytes([self.part.rank + 1]) * 64
+
+    def attach_blob(self, peer_rank, blob):
+        self.attached[peer_rank] = blob
+
+
+def _attach_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from srcfd import slab
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = _FakeSlab(world, rank)
+    slab.attach_distributed(s)
+    q.put((rank, {k: v[:2] for k, v in s.attached.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_attach_distributed_hands_every_peer_blob_to_every_rank():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_attach_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60); assert p.exitcode == 0
+    assert got[0] == {1: bytes([2, 2])} and got[1] == {0: bytes([1, 1])}      # everybody else's blob, never its own
+
+
+def test_slab_entry_points_reject_bad_arguments_without_a_gpu():
+    """The srcfd_slab_* entry points are exported and fail with an argument error (no crash, no CPU fallback) on null input."""
+    import ctypes as C
+    from srcfd import _capi as capi
+    L = capi.lib()
+    arr = (C.c_void_p * 1)(None)
+    crit = (C.c_double * 3)(1e-6, 1e-6, 1e-6)
+    assert L.srcfd_slab_step(arr, C.c_int(1), C.c_int64(1), crit) == capi.ERR_ARG
+    assert L.srcfd_slab_step(None, C.c_int(0), C.c_int64(1), crit) == capi.ERR_ARG
+    assert L.srcfd_slab_solve_pressure(arr, C.c_int(1), None, None) == capi.ERR_ARG
+    assert L.srcfd_slab_exchange(arr, C.c_int(1), C.c_int(2)) == capi.ERR_ARG
+    assert b"slab" in L.srcfd_last_error()
+    assert L.srcfd_slab_configure(None, C.c_int(2), C.c_int(0), C.c_int(64), C.c_int(8)) == capi.ERR_ARG
+    p = SlabPartition(100, 4, 3, 8)
+    assert (p.own0, p.own1, p.lo, p.hi, p.nx_local) == (76, 100, 8, 0, 33) and p.global_rows() == (67, 101)
