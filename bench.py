@@ -222,10 +222,10 @@ LG_N = 4096
 BYTES_PER_LUP_MOMENTUM = 40.0     # phi, phi_old, 2 face fluxes, write phi
 
 
-def _ldc_params(n, device, inner_max, tol, scheme_quick=True, Re=1000.0):
+def _ldc_params(n, device, inner_max, tol, scheme_quick=True, Re=1000.0, nx=None):
     from srcfd import _capi as capi
     p = capi.Params()
-    p.nx = p.ny = n
+    p.nx, p.ny = (nx or n), n
     p.dx = p.dy = 1.0 / n
     p.volp = p.dx * p.dy
     p.dt, p.nu, p.rho = 1e-3, 1.0 / Re, 1.0
@@ -238,9 +238,9 @@ def _ldc_params(n, device, inner_max, tol, scheme_quick=True, Re=1000.0):
     return p
 
 
-def _synthetic_rows(n, g0, g1):
-    """Rows g0..g1 of the synthetic 4096^2 state (seeded per GLOBAL row, so every world size sees the same field):
-    p ~ U(-1,1), face fluxes ~ 1e-3 U(-1,1) with exactly zero boundary-face fluxes along i (wall)."""
+def _synthetic_rows(n, g0, g1, nx=None):
+    """Rows g0..g1 of the synthetic nx x n state (nx = n unless given; seeded per GLOBAL row, so every world size sees the
+    same field): p ~ U(-1,1), face fluxes ~ 1e-3 U(-1,1) with exactly zero boundary-face fluxes along i (wall)."""
     Var = np.zeros((3, g1 - g0 + 1, n + 2)); Ff = np.zeros((4, g1 - g0 + 1, n + 2))
     for r in range(g0, g1 + 1):
         rr = np.random.default_rng(1000 + r)
@@ -248,7 +248,7 @@ def _synthetic_rows(n, g0, g1):
         Var[:2, r - g0] = 0.1 * rr.uniform(-1, 1, (2, n + 2))
         Ff[:, r - g0] = 1e-3 * rr.uniform(-1, 1, (4, n + 2))
         if r == 1: Ff[2, r - g0] = 0.0
-        if r == n: Ff[0, r - g0] = 0.0
+        if r == (nx or n): Ff[0, r - g0] = 0.0
     return Var, Ff
 
 
@@ -383,6 +383,28 @@ def slab_record(rank, world, local, dist, torch):
         del Var, Ff
         s.close()
     out["pressure"]["slab_parity"] = parity
+    # ---- the same relaxation with the work per GPU held fixed: a (4096 x N) x 4096 plane, 4096 rows per rank (weak scaling).
+    # 4096^2 over 8 ranks leaves 2.2 M cells = ~35 us of work per rank and pass, the size of the launch / hand-off latencies;
+    # this record shows the exchange itself does not cost throughput when a rank has a GPU's worth of rows.
+    if world > 1:
+        s = slab.GpuSlab(_ldc_params(n, local, 1000, 0.0, nx=n * world), world, rank, halo=halo)
+        slab.attach_distributed(s)
+        g0, g1 = s.part.global_rows()
+        Var, Ff = _synthetic_rows(n, g0, g1, nx=n * world)
+        s.h.upload(Var=Var, VarOld=Var, Ff=Ff)
+        del Var, Ff
+        slab.solve_pressure([s])
+        s.h.synchronize()
+        dist.barrier()
+        s.h.timer_start()
+        sww, _ = slab.solve_pressure([s])
+        msw = maxtime(s.h.timer_stop())
+        s.close()
+        vw = float(n) * n * world * sww / (msw * 1e-3) / 1e9
+        out["pressure_weak"] = {"grid": [n * world, n], "rows_per_gpu": n, "sweeps": sww, "ms": msw, "value": vw, "unit": "GLUP/s",
+                                "scaling": "weak", "per_gpu": vw / world,
+                                "roofline": {"bound": "hbm", "achieved": BYTES_PER_LUP_PRESSURE * vw, "peak": peak * world, "unit": "GB/s",
+                                             "frac": BYTES_PER_LUP_PRESSURE * vw / (peak * world)}}
     # ---- configs[3] proper: 10 outer iterations of the Re=1000 cavity (QUICK, zero start, inner tol 1e-6 / cap 1000)
     its = 10
     s = slab.GpuSlab(_ldc_params(n, local, 1000, 1e-6), world, rank, halo=halo)
