@@ -171,10 +171,10 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         JtbArgs ja;
         ja.s = slab_solve_args(h, 2, 2); ja.partials = h->jtb_partials;
         for (int t = 0; t < nsw;) {
-            // the streaming kernel wants one >= 64-row chunk per warp slot (measured: 4096 columns x 2048+ rows per GPU
-            // 210-280 GLUP/s against 182-200 for the tile kernel; 544 rows per GPU 700 against 805-930): thin slabs keep tiles
+            // thin slabs keep the tile kernel: the streaming kernel needs about 32 rows per warp-slot chunk to pay for its
+            // lead-in rows (4096 columns: from 1024 local rows on; at 544 rows both kernels run at ~118 GLUP/s)
             const int strips4 = (h->K.ny + 55) / 56, slots = h->num_sms * 2 * JTB2_WARPS;
-            const bool roomy = S->force_stream || h->K.nx >= 64 * std::max(1, slots / strips4);
+            const bool roomy = S->force_stream || h->K.nx >= 32 * std::max(1, slots / strips4);
             const bool stream = h->jtb_impl == 2 && !S->use_tiles && roomy;
             int m = std::min(stream ? 4 : h->jtb_H, nsw - t);
             const double* sp = slab_buf(h, k, src);
@@ -320,7 +320,7 @@ static int slab_inner_solve(SlabGroup& G, int op, int k, int slot, int* sweeps_o
         if (op == OP_PRESSURE && h->jtb_impl == 2) {         // which pressure kernel the NEXT solves of this rank use (see SlabState)
             SlabState* S = h->slab;
             const double frac = S->warp_steps > 0 ? (double)S->sc_host->retries / (double)S->warp_steps : 0.0;
-            if (!S->use_tiles) { S->stream_solves += 1; if (frac > 1e-4) S->use_tiles = true; }
+            if (!S->use_tiles) { S->stream_solves += 1; if (frac > 1e-4 && !S->force_stream) S->use_tiles = true; }
             else { S->tile_solves += 1; if (frac < 1e-6) S->use_tiles = false; }
         }
         if (final_buf != 0)
@@ -393,7 +393,7 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     S->lo = lo; S->hi = hi; S->own0 = lo + 1; S->own1 = lo + n_own;
     S->guess[2] = h->p.inner_max;
     if (const char* e = getenv("SRCFD_SLAB_BLOCK")) S->block_cap = atoi(e);
-    if (const char* e = getenv("SRCFD_JTB2_FORCE")) S->force_stream = atoi(e) != 0;
+    if (const char* e = getenv("SRCFD_JTB2_FORCE")) { S->force_stream = atoi(e) != 0; if (S->force_stream) S->use_tiles = false; }   // no probe solve either
     S->mail_bytes = slab_mail_bytes(std::max(1, S->halo), h->K.pitch);
     auto bail = [&](int rc) { std::string keep = g_err; slab_release(h); g_err = keep; return rc; };
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(SRCFD_ERR_CUDA); } } while (0)

@@ -94,6 +94,7 @@ struct srcfd_handle {
     unsigned* jtb_ticket = nullptr;     // last-CTA-done counter of the single-pass kernel
     bool jtb_ghosts_valid = false;      // boundary cells of the scratch plane match the pressure plane
     const void* jtb_pass_fn = nullptr;
+    int jtb2_rb_env = 0;                // SRCFD_JTB2_RB: rows per chunk of the streaming kernel (experiments)
     int jtb_impl = 2;                   // SRCFD_JTB_IMPL: 2 = warp-streaming kernel (k_jtb2_pass), 1 = shared-memory tile kernel
     double* jtb2_partials = nullptr;    // [4][units] per-(sweep, warp-unit) residual sums
     size_t jtb2_units_cap = 0;
@@ -403,6 +404,7 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     CKB(cudaMalloc(&h->prog2, sizeof(int) * ((size_t)h->inner_cap * maxbands + 64)));
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
     if (const char* e = getenv("SRCFD_JTB_IMPL")) h->jtb_impl = atoi(e);
+    if (const char* e = getenv("SRCFD_JTB2_RB")) h->jtb2_rb_env = std::max(1, atoi(e));
     h->jtb2_units_cap = (size_t)((h->p.ny + 55) / 56 + 1) * (size_t)((h->p.nx + 31) / 32 + 1);
     CKB(cudaMalloc(&h->jtb2_partials, sizeof(double) * 4 * h->jtb2_units_cap));
     if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream));
@@ -603,11 +605,13 @@ static int l_jtb2_pass(srcfd_handle* h, const JtbArgs& ja, const double* src, do
     g.own_cols = 64 - 2 * nsw;
     g.n_strips = (h->K.ny + g.own_cols - 1) / g.own_cols;
     const int slots = h->num_sms * 2 * JTB2_WARPS;
-    // one unit per warp slot when the rows allow chunks of >= 64 rows (fewer, longer units: less lead-in redundancy)
-    int chunks = std::max(1, slots / g.n_strips);
-    int RB = std::max(64, (h->K.nx + chunks - 1) / chunks);
-    if (h->K.nx < 64 * chunks) RB = std::max(32, (h->K.nx + 2 * chunks - 1) / (2 * chunks));   // small planes: shorter chunks, more warps
-    if (const char* e = getenv("SRCFD_JTB2_RB")) RB = std::max(1, atoi(e));
+    // Rows per chunk: as many chunks as give ONE unit per warp slot (all units resident in a single round), at least 32 rows.
+    // The kernel is very sensitive to this (measured, 4096 columns, 2368 slots, 74 strips -> 32 chunks): 4096 rows: 128 rows per
+    // chunk 267 GLUP/s, 112 (1.16 units per slot: a second round) 176, 144 (0.9) 238; 2064 rows: 72 (0.9) 211, 64 (1.03) 198,
+    // 56 156, 128 160; 1056 rows: 40 (0.84) 173, 48 155, 56 142.
+    const int chunks0 = std::max(1, slots / g.n_strips);
+    int RB = std::max(32, (h->K.nx + chunks0 - 1) / chunks0);
+    if (h->jtb2_rb_env > 0) RB = h->jtb2_rb_env;
     g.RB = RB; g.n_chunks = (h->K.nx + RB - 1) / RB;
     const long long units = (long long)g.n_strips * g.n_chunks;
     if ((size_t)units > h->jtb2_units_cap) return fail(SRCFD_ERR_ARG, "jtb2: partial-sum buffer too small");

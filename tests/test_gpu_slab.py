@@ -54,8 +54,19 @@ def _close(slabs):
         s.close()
 
 
+@pytest.fixture(params=["tiles", "stream"])
+def pressure_kernel(request, monkeypatch):
+    """Both pressure kernels of the slab path: the shared-memory tile kernel (what thin planes like these tests' get by
+    default) and the warp-streaming kernel (forced: no probe solve, no fallback)."""
+    if request.param == "stream":
+        monkeypatch.setenv("SRCFD_JTB2_FORCE", "1")
+    else:
+        monkeypatch.delenv("SRCFD_JTB2_FORCE", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_slab_pressure_matches_oracle(world):
+def test_slab_pressure_matches_oracle(world, pressure_kernel):
     from srcfd import slab
     nx, ny = 120, 70
     rng = np.random.default_rng(1)
@@ -74,6 +85,8 @@ def test_slab_pressure_matches_oracle(world):
         assert abs(rms - hist[-1]) <= 1e-12 * abs(hist[-1]), (rms, hist[-1])
         if world > 1 and cap > 8:
             assert slabs[0].info()["exchanges"] >= 2 and slabs[0].info()["halo_bytes"] > 0
+        ks = slabs[0].kernel_stats()
+        assert (ks["stream_solves"], ks["tile_solves"]) == ((1, 0) if pressure_kernel == "stream" else (0, 1))
         _close(slabs)
 
 
@@ -110,7 +123,7 @@ def _cases():
 
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("which", [0, 1])
-def test_slab_outer_iterations_match_oracle(world, which):
+def test_slab_outer_iterations_match_oracle(world, which, pressure_kernel):
     """srcfd_slab_step: whole outer iterations (momentum x2, interpolation, pressure, relaxation, BCs, correction, flux
     update, residual norms) decomposed -- fields bit-equal to the single-domain JACOBI-order oracle."""
     from srcfd import slab
