@@ -317,6 +317,9 @@ __global__ void k_jacobi_tb_commit(SolveArgs a) {
 #ifndef JTB2_PF
 #define JTB2_PF 0
 #endif
+#ifndef JTB2_MINB1
+#define JTB2_MINB1 2      // resident CTAs per SM of the one-column-per-lane variant (3 = 80 registers with spills: 97 against 157 GLUP/s on 544 rows)
+#endif
 constexpr int JTB2_THREADS = JTB2_T, JTB2_WARPS = JTB2_THREADS / 32;
 
 // Second try for a pair of cells whose fast division missed its range test: zero numerators (fields at rest) are exact
@@ -334,7 +337,7 @@ __device__ __noinline__ Jtb2Pair jtb2_retry_pair(double cA, double dnA, double u
 }
 
 struct Jtb2Geom {
-    int own_cols;     // 64 - 2*NL
+    int own_cols;     // 32*C - 2*NL
     int n_strips, n_chunks, RB;
 };
 
@@ -348,16 +351,18 @@ struct Jtb2Lane {     // what a lane knows about its two columns
 // tests, and the 3-row windows / the 3 rows in flight rotate by NAME -- PH = step mod 3 is a template argument, so the
 // slot indices are compile-time and nothing is moved.  Level L keeps row rho in slot (rho - i0 + L) mod 3, which makes
 // "written this step" = PH, "centre" = PH+2, "row above" = PH+1 at every level.
-template <int NL, int PH>
+// C = columns per lane: 2 (64-column strips, the default) or 1 (32-column strips: twice the units for thin slabs, where
+// the two-column form cannot fill the warp slots with chunks long enough to pay for their lead-in rows).
+template <int NL, int PH, int C>
 __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], double (&wB)[NL][3], double (&rqA)[NL + 1], double (&rqB)[NL + 1],
                                                double (&acc)[NL], double (&nA)[3], double (&nB)[3], const double*& pA,
                                                const double*& qA, double*& oA, const int pitch, const Jtb2Lane& L, const double volp,
                                                const Gs3Div& D, const int ra, const int rb, const int sr0, const int sr1,
                                                const int i_valid, unsigned long long* __restrict__ retries) {
     constexpr int NEW = PH, UP = (PH + 1) % 3, CEN = (PH + 2) % 3;
-    const double curA = nA[PH], curB = nB[PH];
+    const double curA = nA[PH], curB = (C == 2) ? nB[PH] : 0.0;
     nA[PH] = L.inA ? __ldcg(pA + 3 * pitch) : 0.0;                    // row i+3 of the plane
-    nB[PH] = L.inB ? __ldcg(pA + 3 * pitch + 1) : 0.0;
+    if (C == 2) nB[PH] = L.inB ? __ldcg(pA + 3 * pitch + 1) : 0.0;
 #if JTB2_PF > 0
     if (L.inA) {                                                      // rows further ahead: into L2 only (no registers held)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pA + (3 + JTB2_PF) * pitch));
@@ -366,12 +371,13 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
 #endif
     // right-hand side: rqX[t] = row i-1-t.  Row i is requested now and first used (as rqX[0]) one step from now.
 #pragma unroll
-    for (int t = NL - 1; t > 0; --t) { rqA[t] = rqA[t - 1]; rqB[t] = rqB[t - 1]; }
-    rqA[0] = rqA[NL]; rqB[0] = rqB[NL];
+    for (int t = NL - 1; t > 0; --t) { rqA[t] = rqA[t - 1]; if (C == 2) rqB[t] = rqB[t - 1]; }
+    rqA[0] = rqA[NL];
     rqA[NL] = L.inA ? __ldg(qA) : 0.0;
-    rqB[NL] = L.inB ? __ldg(qA + 1) : 0.0;
+    if (C == 2) { rqB[0] = rqB[NL]; rqB[NL] = L.inB ? __ldg(qA + 1) : 0.0; }
     pA += pitch; qA += pitch;
-    wA[0][NEW] = curA; wB[0][NEW] = curB;
+    wA[0][NEW] = curA;
+    if (C == 2) wB[0][NEW] = curB;
     // All NL levels are computed without a branch between them (level t+1 needs level t only as its "row below", so most
     // of its arithmetic overlaps level t); a division that missed its range test is noticed ONCE, at the end of the step,
     // and the step is then redone level by level with the zero-safe / IEEE path -- every input of the redo is intact:
@@ -381,25 +387,27 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
 #pragma unroll
     for (int t = 1; t <= NL; ++t) {
         const int r = i - t;
-        const double cA = wA[t - 1][CEN], cB = wB[t - 1][CEN];
-        const double lft = __shfl_up_sync(0xffffffffu, cB, 1);
-        const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);
-        double RA, RB_;
+        const double cA = wA[t - 1][CEN], cB = (C == 2) ? wB[t - 1][CEN] : 0.0;
+        const double lft = __shfl_up_sync(0xffffffffu, C == 2 ? cB : cA, 1);     // column jA - 1
+        const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);                 // column jB + 1 (C = 1: jA + 1)
+        double RA, RB_ = 0.0;
         bool failA = false, failB = false;
         // plain range test: a widened test that lets exact +0 numerators pass (two integer instructions per division) was
         // measured at 170 against 267 GLUP/s on the same box -- fields with zeros or denormals are the tile kernel's job
-        const double xA = pressure_cell3(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, lft, rqA[t - 1], volp, D, RA, failA);
-        const double xB = pressure_cell3(cB, wB[t - 1][NEW], wB[t - 1][UP], rgt, cA, rqB[t - 1], volp, D, RB_, failB);
+        const double xA = pressure_cell3(cA, wA[t - 1][NEW], wA[t - 1][UP], C == 2 ? cB : rgt, lft, rqA[t - 1], volp, D, RA, failA);
+        double xB = 0.0;
+        if (C == 2) xB = pressure_cell3(cB, wB[t - 1][NEW], wB[t - 1][UP], rgt, cA, rqB[t - 1], volp, D, RB_, failB);
         // a miss only matters in an interior column (the out-of-plane lanes of an edge strip hold zeros and always miss)
         // and once the level is fed by streamed rows (the first 2t steps of a chunk compute lead-in garbage)
-        bad = bad || (((failA && L.intA) || (failB && L.intB)) && i - i_valid >= 2 * t);
+        bad = bad || (((failA && L.intA) || (C == 2 && failB && L.intB)) && i - i_valid >= 2 * t);
         const double nvA = L.intA ? xA : cA, nvB = L.intB ? xB : cB;
-        ss[t - 1] = RA * RA + RB_ * RB_;                              // a lane owns both of its columns or neither
+        ss[t - 1] = (C == 2) ? RA * RA + RB_ * RB_ : RA * RA;         // a lane owns both of its columns or neither
         if (t < NL) {
-            wA[t][NEW] = nvA; wB[t][NEW] = nvB;
+            wA[t][NEW] = nvA;
+            if (C == 2) wB[t][NEW] = nvB;
         } else if ((unsigned)(r - ra) <= (unsigned)(rb - ra)) {
             if (L.ownA) oA[0] = nvA;
-            if (L.ownB) oA[1] = nvB;
+            if (C == 2 && L.ownB) oA[1] = nvB;
         }
     }
     if (__builtin_expect(__any_sync(0xffffffffu, bad), 0)) {
@@ -407,18 +415,22 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
 #pragma unroll
         for (int t = 1; t <= NL; ++t) {
             const int r = i - t;
-            const double cA = wA[t - 1][CEN], cB = wB[t - 1][CEN];
-            const double lft = __shfl_up_sync(0xffffffffu, cB, 1);
+            const double cA = wA[t - 1][CEN], cB = (C == 2) ? wB[t - 1][CEN] : 0.0;
+            const double lft = __shfl_up_sync(0xffffffffu, C == 2 ? cB : cA, 1);
             const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);
-            const Jtb2Pair o = jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, wB[t - 1][NEW], wB[t - 1][UP], lft, rgt,
-                                               rqA[t - 1], rqB[t - 1], volp, D);
+            // C = 1: the "B cell" of the pair routine is fed the A cell's own operands and ignored
+            const Jtb2Pair o = (C == 2) ? jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], cB, wB[t - 1][NEW], wB[t - 1][UP], lft, rgt,
+                                                          rqA[t - 1], rqB[t - 1], volp, D)
+                                        : jtb2_retry_pair(cA, wA[t - 1][NEW], wA[t - 1][UP], rgt, wA[t - 1][NEW], wA[t - 1][UP], lft, rgt,
+                                                          rqA[t - 1], rqA[t - 1], volp, D);
             const double nvA = L.intA ? o.xA : cA, nvB = L.intB ? o.xB : cB;
-            ss[t - 1] = o.RA * o.RA + o.RB * o.RB;
+            ss[t - 1] = (C == 2) ? o.RA * o.RA + o.RB * o.RB : o.RA * o.RA;
             if (t < NL) {
-                wA[t][NEW] = nvA; wB[t][NEW] = nvB;
+                wA[t][NEW] = nvA;
+                if (C == 2) wB[t][NEW] = nvB;
             } else if ((unsigned)(r - ra) <= (unsigned)(rb - ra)) {
                 if (L.ownA) oA[0] = nvA;
-                if (L.ownB) oA[1] = nvB;
+                if (C == 2 && L.ownB) oA[1] = nvB;
             }
         }
     }
@@ -428,8 +440,8 @@ __device__ __forceinline__ void jtb2_fast_step(int i, double (&wA)[NL][3], doubl
     oA += pitch;
 }
 
-template <int NL>
-__global__ void __launch_bounds__(JTB2_THREADS, JTB2_MINB) k_jtb2_pass(JtbArgs ja, const double* __restrict__ src, double* __restrict__ dst,
+template <int NL, int C>
+__global__ void __launch_bounds__(JTB2_THREADS, (C == 1) ? JTB2_MINB1 : JTB2_MINB) k_jtb2_pass(JtbArgs ja, const double* __restrict__ src, double* __restrict__ dst,
                                                                        Jtb2Geom g, int res_r0, int res_r1, double* __restrict__ partials,
                                                                        double* __restrict__ sums, unsigned* __restrict__ ticket,
                                                                        const int* __restrict__ done,
@@ -447,16 +459,16 @@ __global__ void __launch_bounds__(JTB2_THREADS, JTB2_MINB) k_jtb2_pass(JtbArgs j
     const int pitch = K.pitch;
     for (int u = blockIdx.x * JTB2_WARPS + warp; u < n_units; u += gridDim.x * JTB2_WARPS) {
         const int s = u % g.n_strips, ch = u / g.n_strips;
-        const int jA = 1 + s * g.own_cols - NL + 2 * lane, jB = jA + 1;
+        const int jA = 1 + s * g.own_cols - NL + C * lane, jB = jA + 1;
         const int ra = 1 + ch * g.RB, rb = min(K.nx, ra + g.RB - 1);
         const int i_start = max(0, ra - NL), i_end = rb + NL;
         Jtb2Lane L;
-        L.inA = jA >= 0 && jA <= K.ny + 1; L.inB = jB >= 0 && jB <= K.ny + 1;
-        L.intA = jA >= 1 && jA <= K.ny; L.intB = jB >= 1 && jB <= K.ny;
-        L.ownA = L.intA && 2 * lane >= NL && 2 * lane < NL + g.own_cols;
+        L.inA = jA >= 0 && jA <= K.ny + 1; L.inB = C == 2 && jB >= 0 && jB <= K.ny + 1;
+        L.intA = jA >= 1 && jA <= K.ny; L.intB = C == 2 && jB >= 1 && jB <= K.ny;
+        L.ownA = L.intA && C * lane >= NL && C * lane < NL + g.own_cols;
         L.ownB = L.intB && 2 * lane + 1 >= NL && 2 * lane + 1 < NL + g.own_cols;
         // a lane that owns exactly one of its two columns (odd NL, odd ny): the unit masks cell by cell in the generic steps
-        const bool split = __any_sync(0xffffffffu, L.ownA != L.ownB);
+        const bool split = C == 2 && __any_sync(0xffffffffu, L.ownA != L.ownB);
         int sr0 = max(ra, res_r0), sr1 = min(rb, res_r1);             // rows whose residual this unit counts
         if (sr1 < sr0) sr0 = sr1 = 0x3fffffff;                        // none: keeps the unsigned range test of the steady-state step false
         const int i_valid = (ra - NL <= 0) ? -0x3fffffff : i_start;   // level t is fed by streamed rows from step i_valid + 2t on
@@ -508,18 +520,23 @@ __global__ void __launch_bounds__(JTB2_THREADS, JTB2_MINB) k_jtb2_pass(JtbArgs j
                 const int r = i - t;                                  // row computed at this level (warp-uniform)
                 double nvA = wA[t - 1][1], nvB = wB[t - 1][1];        // not interior: the value passes through
                 if (r >= i_start && r <= K.nx + 1) {
-                    const double cA = wA[t - 1][1], cB = wB[t - 1][1];
-                    const double lft = __shfl_up_sync(0xffffffffu, cB, 1);       // column jA - 1
-                    const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);     // column jB + 1
+                    const double cA = wA[t - 1][1], cB = (C == 2) ? wB[t - 1][1] : 0.0;
+                    const double lft = __shfl_up_sync(0xffffffffu, C == 2 ? cB : cA, 1);     // column jA - 1
+                    const double rgt = __shfl_down_sync(0xffffffffu, cA, 1);                 // column jB + 1 (C = 1: jA + 1)
                     if (r >= 1 && r <= K.nx) {
-                        double RA, RB_;
+                        double RA, RB_ = 0.0;
                         bool f1 = false, f2 = false;
-                        double xA = pressure_cell3z(cA, wA[t - 1][2], wA[t - 1][0], cB, lft, rqA[t - 1], volp, D, RA, f1);
-                        double xB = pressure_cell3z(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D, RB_, f2);
+                        const double jpA = (C == 2) ? cB : rgt;
+                        double xA = pressure_cell3z(cA, wA[t - 1][2], wA[t - 1][0], jpA, lft, rqA[t - 1], volp, D, RA, f1);
+                        double xB = 0.0;
+                        if (C == 2) xB = pressure_cell3z(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D, RB_, f2);
                         if (__builtin_expect((f1 && L.intA) || (f2 && L.intB), 0)) {
-                            const double2 o1 = pressure_cell3_ieee(cA, wA[t - 1][2], wA[t - 1][0], cB, lft, rqA[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
-                            const double2 o2 = pressure_cell3_ieee(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
-                            xA = o1.x; RA = o1.y; xB = o2.x; RB_ = o2.y;
+                            const double2 o1 = pressure_cell3_ieee(cA, wA[t - 1][2], wA[t - 1][0], jpA, lft, rqA[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
+                            xA = o1.x; RA = o1.y;
+                            if (C == 2) {
+                                const double2 o2 = pressure_cell3_ieee(cB, wB[t - 1][2], wB[t - 1][0], rgt, cA, rqB[t - 1], volp, D.dx2.b, D.dy2.b, D.apd.b);
+                                xB = o2.x; RB_ = o2.y;
+                            }
                         }
                         if (L.intA) nvA = xA;
                         if (L.intB) nvB = xB;
@@ -557,9 +574,9 @@ __global__ void __launch_bounds__(JTB2_THREADS, JTB2_MINB) k_jtb2_pass(JtbArgs j
                     nA[2] = L.inA ? __ldcg(pA + 2 * pitch) : 0.0;
                     nB[2] = L.inB ? __ldcg(pA + 2 * pitch + 1) : 0.0;
                     for (int m = 0; m < nfast; m += 3, i += 3) {
-                        jtb2_fast_step<NL, 0>(i, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
-                        jtb2_fast_step<NL, 1>(i + 1, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
-                        jtb2_fast_step<NL, 2>(i + 2, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                        jtb2_fast_step<NL, 0, C>(i, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                        jtb2_fast_step<NL, 1, C>(i + 1, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
+                        jtb2_fast_step<NL, 2, C>(i + 2, wA, wB, rqA, rqB, acc, nA, nB, pA, qA, oA, pitch, L, volp, D, ra, rb, sr0, sr1, i_valid, retries);
                     }
                     n0A = nA[0]; n0B = nB[0];                          // rows i, i+1 for the generic steps (row i+2 is re-requested there)
                     n1A = nA[1]; n1B = nB[1];

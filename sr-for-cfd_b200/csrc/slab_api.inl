@@ -171,10 +171,12 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         JtbArgs ja;
         ja.s = slab_solve_args(h, 2, 2); ja.partials = h->jtb_partials;
         for (int t = 0; t < nsw;) {
-            // thin slabs keep the tile kernel: the streaming kernel needs about 32 rows per warp-slot chunk to pay for its
-            // lead-in rows (4096 columns: from 1024 local rows on; at 544 rows both kernels run at ~118 GLUP/s)
-            const int strips4 = (h->K.ny + 55) / 56, slots = h->num_sms * 2 * JTB2_WARPS;
-            const bool roomy = S->force_stream || h->K.nx >= 32 * std::max(1, slots / strips4);
+            // Very thin slabs keep the tile kernel.  Measured per-rank compute on 4096 columns (tools/thin_slab_probe.py,
+            // GLUP/s streaming / tiles): 288 rows 97 / 101, 544 rows 156 / 118 (one column per lane), 800 rows 184 / 127,
+            // 1056 rows 197 / 137, 2064 rows 228 / 147, 4096 rows 267 / 152 -- the streaming kernel from ~12 rows per
+            // two-column warp-slot chunk on (384 rows at 4096 columns).
+            const int strips4 = (h->K.ny + 55) / 56, slots = h->num_sms * JTB2_MINB * JTB2_WARPS;
+            const bool roomy = S->force_stream || h->K.nx >= 12 * std::max(1, slots / strips4);
             const bool stream = h->jtb_impl == 2 && !S->use_tiles && roomy;
             int m = std::min(stream ? 4 : h->jtb_H, nsw - t);
             const double* sp = slab_buf(h, k, src);

@@ -94,6 +94,7 @@ struct srcfd_handle {
     unsigned* jtb_ticket = nullptr;     // last-CTA-done counter of the single-pass kernel
     bool jtb_ghosts_valid = false;      // boundary cells of the scratch plane match the pressure plane
     const void* jtb_pass_fn = nullptr;
+    int jtb2_cols_env = 0;              // SRCFD_JTB2_COLS: 1 | 2 columns per lane of the streaming kernel (experiments; 0 = by size)
     int jtb2_rb_env = 0;                // SRCFD_JTB2_RB: rows per chunk of the streaming kernel (experiments)
     int jtb_impl = 2;                   // SRCFD_JTB_IMPL: 2 = warp-streaming kernel (k_jtb2_pass), 1 = shared-memory tile kernel
     double* jtb2_partials = nullptr;    // [4][units] per-(sweep, warp-unit) residual sums
@@ -405,7 +406,8 @@ int srcfd_create(const srcfd_params* params, srcfd_handle** out) {
     if (const char* e = getenv("SRCFD_PAIR")) h->pair_momentum = atoi(e) != 0;
     if (const char* e = getenv("SRCFD_JTB_IMPL")) h->jtb_impl = atoi(e);
     if (const char* e = getenv("SRCFD_JTB2_RB")) h->jtb2_rb_env = std::max(1, atoi(e));
-    h->jtb2_units_cap = (size_t)((h->p.ny + 55) / 56 + 1) * (size_t)((h->p.nx + 31) / 32 + 1);
+    if (const char* e = getenv("SRCFD_JTB2_COLS")) h->jtb2_cols_env = atoi(e);
+    h->jtb2_units_cap = (size_t)((h->p.ny + 23) / 24 + 1) * (size_t)((h->p.nx + 15) / 16 + 1);   // 24 = owned columns of a 32-column strip at 4 sweeps; chunks of >= 16 rows
     CKB(cudaMalloc(&h->jtb2_partials, sizeof(double) * 4 * h->jtb2_units_cap));
     if (h->jtb_H) { CKB(cudaMalloc(&h->jtb_partials, sizeof(double) * 2 * 8 * (size_t)(h->jtb_grid + 1))); CKB(cudaMalloc(&h->jtb_sums, sizeof(double) * 8 * 16)); CKB(cudaMemsetAsync(h->jtb_sums, 0, sizeof(double) * 8 * 16, h->stream));
                       CKB(cudaMalloc(&h->jtb_ticket, sizeof(unsigned))); CKB(cudaMemsetAsync(h->jtb_ticket, 0, sizeof(unsigned), h->stream)); }
@@ -601,10 +603,21 @@ static int ev_drain(srcfd_handle* h) {
 static int l_jtb2_pass(srcfd_handle* h, const JtbArgs& ja, const double* src, double* dst, int nsw, int r0, int r1, double* sums,
                        const int* done, unsigned long long* retries, long long* warp_steps) {
     if (nsw < 1 || nsw > 4) return fail(SRCFD_ERR_ARG, "jtb2: 1..4 sweeps per pass");
+    const int slots2 = h->num_sms * JTB2_MINB * JTB2_WARPS;
+    // columns per lane: 2 (64-column strips) unless the one-unit-per-slot chunks would be shorter than 48 rows -- then 1
+    // (32-column strips: more units and half the registers, so more resident warps and longer chunks; measured on 4096
+    // columns: 544 rows 157 GLUP/s against 118 for two columns and for the tile kernel, 1056 rows 197 against 186)
+    int C = 2;
+    {
+        const int strips2 = (h->K.ny + (64 - 2 * nsw) - 1) / (64 - 2 * nsw);
+        if ((h->K.nx + std::max(1, slots2 / strips2) - 1) / std::max(1, slots2 / strips2) < 48) C = 1;
+        if (h->jtb2_cols_env == 1 || h->jtb2_cols_env == 2) C = h->jtb2_cols_env;
+    }
+    const int ctas_per_sm = C == 1 ? JTB2_MINB1 : JTB2_MINB;
+    const int slots = h->num_sms * ctas_per_sm * JTB2_WARPS;
     Jtb2Geom g;
-    g.own_cols = 64 - 2 * nsw;
+    g.own_cols = 32 * C - 2 * nsw;
     g.n_strips = (h->K.ny + g.own_cols - 1) / g.own_cols;
-    const int slots = h->num_sms * 2 * JTB2_WARPS;
     // Rows per chunk: as many chunks as give ONE unit per warp slot (all units resident in a single round), at least 32 rows.
     // The kernel is very sensitive to this (measured, 4096 columns, 2368 slots, 74 strips -> 32 chunks): 4096 rows: 128 rows per
     // chunk 267 GLUP/s, 112 (1.16 units per slot: a second round) 176, 144 (0.9) 238; 2064 rows: 72 (0.9) 211, 64 (1.03) 198,
@@ -615,15 +628,16 @@ static int l_jtb2_pass(srcfd_handle* h, const JtbArgs& ja, const double* src, do
     g.RB = RB; g.n_chunks = (h->K.nx + RB - 1) / RB;
     const long long units = (long long)g.n_strips * g.n_chunks;
     if ((size_t)units > h->jtb2_units_cap) return fail(SRCFD_ERR_ARG, "jtb2: partial-sum buffer too small");
-    const int grid = (int)std::max<long long>(1, std::min<long long>((units + JTB2_WARPS - 1) / JTB2_WARPS, (long long)h->num_sms * 2));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((units + JTB2_WARPS - 1) / JTB2_WARPS, (long long)h->num_sms * ctas_per_sm));
     const int cap = h->p.max_ctas > 0 ? h->p.max_ctas : (1 << 30);
     const dim3 gd(std::min(grid, cap));
-    switch (nsw) {
-        case 1: k_jtb2_pass<1><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
-        case 2: k_jtb2_pass<2><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
-        case 3: k_jtb2_pass<3><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
-        default: k_jtb2_pass<4><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries); break;
+#define JTB2_LAUNCH(NLv, Cv) k_jtb2_pass<NLv, Cv><<<gd, JTB2_THREADS, 0, h->stream>>>(ja, src, dst, g, r0, r1, h->jtb2_partials, sums, h->jtb_ticket, done, retries)
+    if (C == 2) {
+        switch (nsw) { case 1: JTB2_LAUNCH(1, 2); break; case 2: JTB2_LAUNCH(2, 2); break; case 3: JTB2_LAUNCH(3, 2); break; default: JTB2_LAUNCH(4, 2); break; }
+    } else {
+        switch (nsw) { case 1: JTB2_LAUNCH(1, 1); break; case 2: JTB2_LAUNCH(2, 1); break; case 3: JTB2_LAUNCH(3, 1); break; default: JTB2_LAUNCH(4, 1); break; }
     }
+#undef JTB2_LAUNCH
     LAUNCH_CHECK(h);
     if (warp_steps) *warp_steps += units * (long long)(g.RB + 2 * nsw) * nsw;
     return SRCFD_OK;

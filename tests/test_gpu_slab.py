@@ -54,14 +54,15 @@ def _close(slabs):
         s.close()
 
 
-@pytest.fixture(params=["tiles", "stream"])
+@pytest.fixture(params=["tiles", "stream", "stream1"])
 def pressure_kernel(request, monkeypatch):
-    """Both pressure kernels of the slab path: the shared-memory tile kernel (what thin planes like these tests' get by
-    default) and the warp-streaming kernel (forced: no probe solve, no fallback)."""
-    if request.param == "stream":
+    """The pressure kernels of the slab path: the shared-memory tile kernel (what thin planes like these tests' get by
+    default) and the warp-streaming kernel with two columns per lane and with one (forced: no probe solve, no fallback)."""
+    monkeypatch.delenv("SRCFD_JTB2_FORCE", raising=False)
+    monkeypatch.delenv("SRCFD_JTB2_COLS", raising=False)
+    if request.param != "tiles":
         monkeypatch.setenv("SRCFD_JTB2_FORCE", "1")
-    else:
-        monkeypatch.delenv("SRCFD_JTB2_FORCE", raising=False)
+        monkeypatch.setenv("SRCFD_JTB2_COLS", "1" if request.param == "stream1" else "2")
     return request.param
 
 
@@ -86,7 +87,7 @@ def test_slab_pressure_matches_oracle(world, pressure_kernel):
         if world > 1 and cap > 8:
             assert slabs[0].info()["exchanges"] >= 2 and slabs[0].info()["halo_bytes"] > 0
         ks = slabs[0].kernel_stats()
-        assert (ks["stream_solves"], ks["tile_solves"]) == ((1, 0) if pressure_kernel == "stream" else (0, 1))
+        assert (ks["stream_solves"], ks["tile_solves"]) == ((0, 1) if pressure_kernel == "tiles" else (1, 0))
         _close(slabs)
 
 
