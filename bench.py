@@ -280,7 +280,7 @@ def large_grid_record(device):
     lups = float(n) * n * sw
     ach = BYTES_PER_LUP_PRESSURE * lups / (ms * 1e-3) / 1e9
     traffic = ncu_value("ncu_jtb_4096_r02.json", "dram_bytes_per_launch")
-    out["pressure"] = {"kernel": "k_jacobi_tb_pass<4> (solve_pressure, 4 sweeps per pass over HBM)", "sweeps": sw, "ms": ms,
+    out["pressure"] = {"kernel": "k_jtb2_pass<4, 2> (solve_pressure, warp-streaming, 4 sweeps per pass over HBM)", "sweeps": sw, "ms": ms,
                        "value": lups / (ms * 1e-3) / 1e9, "unit": "GLUP/s",
                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                     "peak_source": peak_src, "traffic": traffic,

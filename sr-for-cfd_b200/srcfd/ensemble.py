@@ -41,6 +41,7 @@ class CaseResult:
     total_sweeps: List[int]
     rms: List[float]
     fields: Optional[np.ndarray] = None       # (3, ny, nx) u, v, p in the reference's output orientation
+    phases: Optional[Dict[str, float]] = None  # seconds spent constructing the solver, injecting the warm start, solving
 
 
 def multibc_sweep(res_ldc=tuple(range(50, 701, 50)), res_bfs=(100, 200, 400), nx=400, ny=400, max_iterations=2000):
@@ -108,27 +109,45 @@ def warm_start_fields(spec: CaseSpec, sr_files: dict, coarse: Optional[dict] = N
 
 
 def run_case(spec: CaseSpec, device: int = 0, max_ctas: int = 0, sr_files: Optional[dict] = None, keep_fields=True,
-             coarse: Optional[dict] = None, warm: Optional[np.ndarray] = None) -> CaseResult:
+             coarse: Optional[dict] = None, warm: Optional[np.ndarray] = None, pool: Optional[dict] = None) -> CaseResult:
     """Coarse solve -> SR warm start -> fine solve for one case on one GPU (the reference's per-case workflow).
-    `coarse`: this case's coarse fields when coarse_stage already produced them; `warm`: its finished initial guess."""
-    from . import bfs, ldc
+    `coarse`: this case's coarse fields when coarse_stage already produced them; `warm`: its finished initial guess;
+    `pool`: a worker's solvers by (family, grid) -- a sweep re-parameterises one solver per family (Re, BCs, budget:
+    srcfd_set_params) instead of allocating page-locked arrays and device state for every case, which cost as much as
+    30 outer iterations of a 400x400 case; the start state is re-made by _initialize_fields exactly as a new solver's."""
+    from . import bfs, ldc, solver as S
     mod = bfs if spec.kind == "bfs" else ldc
     wf = mod._wf
     t0 = time.time()
     bc = _case_bc(spec)
-    solver = wf._make_solver(spec.Re, spec.nx, spec.ny, *wf._defaults(None, None, None, None)[:2], None,
-                             spec.max_iterations, bc, 1.0, 2.0, 1.0, *wf._defaults(None, None, None, None)[2:], None,
-                             device=device, max_ctas=max_ctas)
+    key = (spec.kind == "bfs", spec.nx, spec.ny, device, max_ctas)
+    solver = pool.get(key) if pool is not None else None
+    if solver is None:
+        solver = wf._make_solver(spec.Re, spec.nx, spec.ny, *wf._defaults(None, None, None, None)[:2], None,
+                                 spec.max_iterations, bc, 1.0, 2.0, 1.0, *wf._defaults(None, None, None, None)[2:], None,
+                                 device=device, max_ctas=max_ctas)
+        if pool is not None:
+            pool[key] = solver
+    else:
+        solver.fluid = S.FluidProperties(Re=spec.Re, rho=1.0)
+        solver.bc = bc or wf._default_bc()
+        solver.settings.max_iterations = spec.max_iterations
+        solver.residual_history = {'u': [], 'v': [], 'p': []}
+        solver._initialize_fields()
+    t1 = time.time()
     if warm is None and spec.warm_start and sr_files is not None:
         warm = warm_start_fields(spec, sr_files, coarse)
     if warm is not None:
         solver._sync_params()
         solver._handle.set_fields(warm)
         solver._handle.download(solver.Var, solver.VarOld, solver.Ff)
+    t2 = time.time()
     n, _ = solver.solve("ensemble", verbose=False, save=False)
+    t3 = time.time()
     fields = np.stack([solver.Var[k, 1:-1, 1:-1].T for k in range(3)]) if keep_fields else None
     return CaseResult(spec.label(), -1, int(n), bool(solver.converged), time.time() - t0,
-                      [int(x) for x in solver.total_sweeps], [float(x) for x in solver.last_rms], fields)
+                      [int(x) for x in solver.total_sweeps], [float(x) for x in solver.last_rms], fields,
+                      dict(construct=t1 - t0, warm=t2 - t1, solve=t3 - t2))
 
 
 def warm_stage(cases: Sequence[CaseSpec], sr_files: dict, device: int = 0) -> List[Optional[np.ndarray]]:
@@ -156,7 +175,8 @@ def warm_stage(cases: Sequence[CaseSpec], sr_files: dict, device: int = 0) -> Li
 
 
 def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 4, num_sms: int = 148,
-              runner: Callable = run_case, warm_fields: Optional[List] = None, **kw) -> List[CaseResult]:
+              runner: Callable = run_case, warm_fields: Optional[List] = None, reuse_solvers: bool = True,
+              **kw) -> List[CaseResult]:
     """Run this rank's cases, `concurrency` at a time, each with 1/concurrency of the SMs.  `warm_fields`: the cases'
     initial guesses when warm_stage ran already."""
     results: List[Optional[CaseResult]] = [None] * len(cases)
@@ -169,6 +189,7 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 4, 
             warm_fields = warm_stage(cases, sr_files, device)      # the workers below only run fine solves
 
     def worker():
+        pool: Dict = {}                                  # this worker's solvers, one per case family (run_case)
         while True:
             with lock:
                 i = nxt[0]
@@ -176,6 +197,8 @@ def run_local(cases: Sequence[CaseSpec], device: int = 0, concurrency: int = 4, 
             if i >= len(cases):
                 return
             extra = dict(warm=warm_fields[i]) if warm_fields[i] is not None else {}
+            if runner is run_case and reuse_solvers:
+                extra["pool"] = pool
             results[i] = runner(cases[i], device=device, max_ctas=max_ctas, **extra, **kw)
 
     threads = [threading.Thread(target=worker) for _ in range(max(1, min(concurrency, len(cases))))]

@@ -91,6 +91,39 @@ def test_slab_pressure_matches_oracle(world, pressure_kernel):
         _close(slabs)
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_slab_pressure_rest_and_denormal_fields(world, pressure_kernel):
+    """A field at rest with a small source (zeros beyond a front that decays into the denormals -- the start of every
+    cavity run) and a field of tiny values: the streaming kernel's rows-at-rest shortcut, its redo path and the scaled
+    division (div_mid) against the oracle, signed zeros included.  The front lies across the lanes of a strip in the
+    first grid and along the rows in the second."""
+    from srcfd import slab
+    rng = np.random.default_rng(5)
+    for nx, ny, lx, ly, cap in ((150, 230, 1.0, 6 * 230 / 150, 220), (230, 150, 6 * 230 / 150, 1.0, 220), (96, 140, 1.0, 1.0, 37)):
+        Var = np.zeros((3, nx + 2, ny + 2)); Ff = np.zeros((4, nx + 2, ny + 2))
+        if cap == 37:
+            Var[2] = rng.uniform(-1, 1, (nx + 2, ny + 2)) * 2.0 ** rng.integers(-1074, -940, (nx + 2, ny + 2))
+            Ff[:] = rng.uniform(-1, 1, Ff.shape) * 2.0 ** rng.integers(-1074, -960, Ff.shape)
+            Var[2, 30:60] = 0.0; Ff[:, 29:61] = 0.0            # rows at rest inside a tiny-valued field
+        else:
+            Ff[:, 3:9, 4:10] = 1e-3 * rng.uniform(-1, 1, (4, 6, 6))
+        dx, dy = lx / nx, ly / ny
+        case = O.Case(nx=nx, ny=ny, lx=lx, ly=ly, dt=1e-3, inner_tol=0.0, inner_max=cap, order=O.ORDER_JACOBI)
+        slabs = _make(case, world, 16, Var=Var, Ff=Ff)
+        n, rms = slab.solve_pressure(slabs)
+        B = Var.copy()
+        m, hist = O.solve_pressure(B, Ff, nx, ny, dx, dy, 1e-3, 1.0, dx * dy, order=O.ORDER_JACOBI, tolerance=0.0, max_iter=cap, rms_hist=True)
+        got = _gather(slabs)[0]
+        assert n == m, (world, nx, ny, n, m)
+        assert np.array_equal(got[2], B[2, 1:-1]), (world, nx, ny, np.max(np.abs(got[2] - B[2, 1:-1])))
+        assert np.array_equal(np.signbit(got[2]), np.signbit(B[2, 1:-1]))
+        assert abs(rms - hist[-1]) <= 1e-12 * abs(hist[-1]) + 1e-300, (rms, hist[-1])
+        if cap > 37:
+            a = np.abs(B[2, 1:-1, 1:-1])
+            assert np.count_nonzero((a > 0) & (a < 2.0 ** -1022)) > 50 and np.count_nonzero(a == 0) > 1000
+        _close(slabs)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
 def test_slab_momentum_matches_oracle(world, scheme):
@@ -114,6 +147,49 @@ def test_slab_momentum_matches_oracle(world, scheme):
             assert n == m, (world, scheme, tol, cap, k, n, m)
             assert np.array_equal(got[k], B[k, 1:-1]), (world, scheme, tol, cap, k, np.max(np.abs(got[k] - B[k, 1:-1])))
             _close(slabs)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
+def test_slab_momentum_with_library_fluxes(world, scheme):
+    """Momentum solves on face fluxes as the library's own kernels leave them (BCs, linear_interpolation, update_flux on
+    every slab's local rows, halo rows included) instead of uploaded ones: the slabs' fluxes equal the undivided ones,
+    the W/S planes are the negated E/N planes of the neighbouring cell, and the solves match the oracle.
+    (A sweep that reads only the two information-bearing planes was measured slower than the four-plane one -- the kernel is
+    latency-bound, not DRAM-bound: 80 against 89 GLUP/s at 4096^2 -- and is not kept.)"""
+    from srcfd import slab, _capi as capi
+    nx, ny = 96, 50
+    rng = np.random.default_rng(4)
+    Var = rng.uniform(-1, 1, (3, nx + 2, ny + 2)); VarOld = Var + 0.01 * rng.uniform(-1, 1, Var.shape)
+    case = O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme=scheme, inner_tol=0.0, inner_max=9, order=O.ORDER_JACOBI)
+
+    def prepare(slabs):
+        for s in slabs:
+            for k in range(3):
+                s.h.k_apply_bc(k)
+            s.h.k_linear_interpolation(); s.h.k_update_flux()
+
+    one = _make(case, 1, 12, Var=Var, VarOld=VarOld)
+    prepare(one)
+    V1 = np.zeros_like(Var); F1 = np.zeros((4, nx + 2, ny + 2))
+    one[0].h.download(Var=V1, Ff=F1)
+    _close(one)
+    assert np.array_equal(F1[2, 2:nx + 1, 1:-1], -F1[0, 1:nx, 1:-1]) and np.array_equal(F1[3, 1:-1, 2:ny + 1], -F1[1, 1:-1, 1:ny])
+    assert np.count_nonzero(F1[0, 1:nx, 1:-1]) > 0.9 * (nx - 1) * ny
+    fn = O.solve_momentum_quick if scheme == "QUICK" else O.solve_momentum_upwind
+    sc = capi.SCHEME_QUICK if scheme == "QUICK" else capi.SCHEME_UPWIND
+    for k in (0, 1):
+        B = V1.copy()
+        m = fn(B, VarOld, F1, k, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0 / 100.0, (1.0 / nx) * (1.0 / ny), order=O.ORDER_JACOBI, tolerance=0.0, max_iter=9)
+        slabs = _make(case, world, 12, Var=Var, VarOld=VarOld)
+        prepare(slabs)
+        if world > 1:
+            assert np.array_equal(_gather(slabs)[2], F1[:, 1:-1])
+        n, _ = slab.solve_momentum(slabs, k, sc)
+        got = _gather(slabs)[0]
+        assert n == m == 9
+        assert np.array_equal(got[k], B[k, 1:-1]), (world, scheme, k, np.max(np.abs(got[k] - B[k, 1:-1])))
+        _close(slabs)
 
 
 def _cases():

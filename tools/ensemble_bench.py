@@ -43,6 +43,7 @@ def main():
         out["runs"].append(dict(concurrency=conc, fine_stage_wall_s=wall, glups=lups / wall / 1e9,
                                 identical_to_first_run=same, iterations=[r.iterations for r in res],
                                 case_seconds=[round(r.seconds, 3) for r in res],
+                                phase_means={k: round(float(np.mean([r.phases[k] for r in res])), 4) for k in ("construct", "warm", "solve")},
                                 case_sweeps=[r.total_sweeps for r in res]))
         print(out["runs"][-1], flush=True)
     print("warm stage", out["warm_stage_s"])
