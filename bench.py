@@ -291,8 +291,11 @@ def large_grid_record(device):
     for scheme, name in ((False, "upwind"), (True, "quick")):
         s = slab.GpuSlab(_ldc_params(n, device, 32, 0.0, scheme_quick=scheme), 1, 0)
         Var, Ff = _synthetic_rows(n, 0, n + 1)
-        s.h.upload(Var=Var, VarOld=Var, Ff=Ff)
+        s.h.upload(Var=Var, VarOld=Var)
         del Var, Ff
+        for k in range(3):                                    # face fluxes as the solver's own kernels leave them: an outer
+            s.h.k_apply_bc(k)                                 # iteration's momentum solves read what the previous iteration's
+        s.h.k_linear_interpolation(); s.h.k_update_flux()     # linear_interpolation + update_flux produced
         sc = capi.SCHEME_QUICK if scheme else capi.SCHEME_UPWIND
         slab.solve_momentum([s], 0, sc)
         s.h.synchronize()
@@ -301,7 +304,8 @@ def large_grid_record(device):
         ms = s.h.timer_stop()
         lups = float(n) * n * sw
         ach = BYTES_PER_LUP_MOMENTUM * lups / (ms * 1e-3) / 1e9
-        out["momentum_" + name] = {"kernel": f"k_slab_sweep<{name}> (one JACOBI sweep per launch)", "sweeps": sw, "ms": ms,
+        out["momentum_" + name] = {"kernel": f"k_slab_sweep<{name}, paired fluxes> (one JACOBI sweep per launch; the west flux is the east flux of the "
+                                             "row above, 48 B of DRAM traffic per cell update against 40 algorithmic)", "sweeps": sw, "ms": ms,
                                    "value": lups / (ms * 1e-3) / 1e9, "unit": "GLUP/s",
                                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
         s.close()

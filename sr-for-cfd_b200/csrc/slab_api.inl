@@ -37,6 +37,7 @@ struct SlabState {
     // back when a tile-kernel solve reports (almost) none.  A handle starts on tiles, i.e. its first solve is the probe.
     bool use_tiles = true;
     bool force_stream = false;    // SRCFD_JTB2_FORCE (experiments): streaming kernel on thin slabs too
+    bool four_faces = false;      // SRCFD_SLAB_FOUR_FACES (tests): momentum sweeps read the stored west-flux plane in every row
     long long warp_steps = 0;     // of the running solve
     int64_t tile_solves = 0, stream_solves = 0;
 };
@@ -201,10 +202,11 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
             double* dp = slab_buf(h, k, dst);
             const int gx = (h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS;
             const dim3 grid(gx, std::max(1, std::min(h->K.nx, (h->num_sms * 8 + gx - 1) / gx)));
-            if (op == OP_UPWIND)
-                k_slab_sweep<OP_UPWIND><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done);
-            else
-                k_slab_sweep<OP_QUICK><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done);
+#define SLAB_SWEEP(OPv, Pv) k_slab_sweep<OPv, Pv><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done)
+            const bool paired = h->ff_paired && !S->four_faces;   // the library's own fluxes (k_slab_sweep)
+            if (op == OP_UPWIND) { if (paired) SLAB_SWEEP(OP_UPWIND, true); else SLAB_SWEEP(OP_UPWIND, false); }
+            else { if (paired) SLAB_SWEEP(OP_QUICK, true); else SLAB_SWEEP(OP_QUICK, false); }
+#undef SLAB_SWEEP
             LAUNCH_CHECK(h);
             src = dst; dst = (dst == o1) ? o2 : o1;
         }
@@ -395,6 +397,7 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     S->lo = lo; S->hi = hi; S->own0 = lo + 1; S->own1 = lo + n_own;
     S->guess[2] = h->p.inner_max;
     if (const char* e = getenv("SRCFD_SLAB_BLOCK")) S->block_cap = atoi(e);
+    if (const char* e = getenv("SRCFD_SLAB_FOUR_FACES")) S->four_faces = atoi(e) != 0;
     if (const char* e = getenv("SRCFD_JTB2_FORCE")) { S->force_stream = atoi(e) != 0; if (S->force_stream) S->use_tiles = false; }   // no probe solve either
     S->mail_bytes = slab_mail_bytes(std::max(1, S->halo), h->K.pitch);
     auto bail = [&](int rc) { std::string keep = g_err; slab_release(h); g_err = keep; return rc; };

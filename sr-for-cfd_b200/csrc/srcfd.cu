@@ -49,6 +49,7 @@ struct srcfd_handle {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     double *Var = nullptr, *VarOld = nullptr, *Ff = nullptr, *rhs = nullptr, *scratch = nullptr;
+    bool ff_paired = false;     // Ff was produced by k_linear_interpolation (+ k_update_flux): W/S planes = negated E/N of the neighbour
     double *partials = nullptr, *res_partials = nullptr, *hist = nullptr;
     void* staging = nullptr;
     size_t staging_bytes = 0;
@@ -472,7 +473,7 @@ int srcfd_upload(srcfd_handle* h, const double* Var, const double* VarOld, const
     const size_t P = (size_t)h->K.plane;
     if (Var) { CK(cudaMemcpyAsync(h->Var, Var, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream)); h->ghosts_fresh = false; h->jtb_ghosts_valid = false; }
     if (VarOld) CK(cudaMemcpyAsync(h->VarOld, VarOld, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, h->stream));
-    if (Ff) CK(cudaMemcpyAsync(h->Ff, Ff, sizeof(double) * 4 * P, cudaMemcpyHostToDevice, h->stream));
+    if (Ff) { CK(cudaMemcpyAsync(h->Ff, Ff, sizeof(double) * 4 * P, cudaMemcpyHostToDevice, h->stream)); h->ff_paired = false; }
     if (residual) CK(cudaMemcpyAsync((char*)h->ctrl + offsetof(Ctrl, residual), residual, sizeof(double) * 3, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // host buffers may be pageable and reused by the caller
     return SRCFD_OK;
@@ -503,7 +504,7 @@ int srcfd_device_ptrs(srcfd_handle* h, uint64_t* Var, uint64_t* VarOld, uint64_t
     CKH(h);
     if (Var) *Var = (uint64_t)(uintptr_t)h->Var;
     if (VarOld) *VarOld = (uint64_t)(uintptr_t)h->VarOld;
-    if (Ff) *Ff = (uint64_t)(uintptr_t)h->Ff;
+    if (Ff) { *Ff = (uint64_t)(uintptr_t)h->Ff; h->ff_paired = false; }   // the caller may write through the pointer
     return SRCFD_OK;
 }
 
@@ -535,6 +536,7 @@ static int l_apply_bc(srcfd_handle* h, int k, int mode = 0) {
 }
 static int l_linear_interpolation(srcfd_handle* h, bool with_rhs) {
     k_linear_interpolation<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->Ff, with_rhs ? h->rhs : nullptr, h->K, h->ctrl);
+    h->ff_paired = true;
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }

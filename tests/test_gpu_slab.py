@@ -151,12 +151,12 @@ def test_slab_momentum_matches_oracle(world, scheme):
 
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
-def test_slab_momentum_with_library_fluxes(world, scheme):
+def test_slab_momentum_with_library_fluxes(world, scheme, monkeypatch):
     """Momentum solves on face fluxes as the library's own kernels leave them (BCs, linear_interpolation, update_flux on
     every slab's local rows, halo rows included) instead of uploaded ones: the slabs' fluxes equal the undivided ones,
-    the W/S planes are the negated E/N planes of the neighbouring cell, and the solves match the oracle.
-    (A sweep that reads only the two information-bearing planes was measured slower than the four-plane one -- the kernel is
-    latency-bound, not DRAM-bound: 80 against 89 GLUP/s at 4096^2 -- and is not kept.)"""
+    the W/S planes are the negated E/N planes of the neighbouring cell -- which lets the sweep take the
+    west flux from the row above instead of loading it (k_slab_sweep<OP, true>) -- and the solves match the oracle with
+    and without that shortcut."""
     from srcfd import slab, _capi as capi
     nx, ny = 96, 50
     rng = np.random.default_rng(4)
@@ -181,15 +181,17 @@ def test_slab_momentum_with_library_fluxes(world, scheme):
     for k in (0, 1):
         B = V1.copy()
         m = fn(B, VarOld, F1, k, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0 / 100.0, (1.0 / nx) * (1.0 / ny), order=O.ORDER_JACOBI, tolerance=0.0, max_iter=9)
-        slabs = _make(case, world, 12, Var=Var, VarOld=VarOld)
-        prepare(slabs)
-        if world > 1:
-            assert np.array_equal(_gather(slabs)[2], F1[:, 1:-1])
-        n, _ = slab.solve_momentum(slabs, k, sc)
-        got = _gather(slabs)[0]
-        assert n == m == 9
-        assert np.array_equal(got[k], B[k, 1:-1]), (world, scheme, k, np.max(np.abs(got[k] - B[k, 1:-1])))
-        _close(slabs)
+        for four in ("0", "1"):
+            monkeypatch.setenv("SRCFD_SLAB_FOUR_FACES", four)
+            slabs = _make(case, world, 12, Var=Var, VarOld=VarOld)
+            prepare(slabs)
+            if world > 1:
+                assert np.array_equal(_gather(slabs)[2], F1[:, 1:-1])
+            n, _ = slab.solve_momentum(slabs, k, sc)
+            got = _gather(slabs)[0]
+            assert n == m == 9
+            assert np.array_equal(got[k], B[k, 1:-1]), (world, scheme, k, four, np.max(np.abs(got[k] - B[k, 1:-1])))
+            _close(slabs)
 
 
 def _cases():
