@@ -304,8 +304,12 @@ def large_grid_record(device):
         ms = s.h.timer_stop()
         lups = float(n) * n * sw
         ach = BYTES_PER_LUP_MOMENTUM * lups / (ms * 1e-3) / 1e9
-        out["momentum_" + name] = {"kernel": f"k_slab_sweep<{name}, paired fluxes> (one JACOBI sweep per launch; the west flux is the east flux of the "
-                                             "row above, 48 B of DRAM traffic per cell update against 40 algorithmic)", "sweeps": sw, "ms": ms,
+        two = os.environ.get("SRCFD_SLAB_SWEEP2", "1") != "0"
+        kern = (f"k_slab_sweep2<{name}, paired fluxes> (two JACOBI sweeps per pass over HBM: register windows per warp, the west flux is the "
+                "east flux of the row above; 24 B of DRAM traffic per cell update against 40 algorithmic)") if two else \
+               (f"k_slab_sweep<{name}, paired fluxes> (one JACOBI sweep per launch; the west flux is the east flux of the "
+                "row above, 48 B of DRAM traffic per cell update against 40 algorithmic)")
+        out["momentum_" + name] = {"kernel": kern, "sweeps": sw, "ms": ms,
                                    "value": lups / (ms * 1e-3) / 1e9, "unit": "GLUP/s",
                                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
         s.close()

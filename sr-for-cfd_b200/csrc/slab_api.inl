@@ -38,6 +38,11 @@ struct SlabState {
     bool use_tiles = true;
     bool force_stream = false;    // SRCFD_JTB2_FORCE (experiments): streaming kernel on thin slabs too
     bool four_faces = false;      // SRCFD_SLAB_FOUR_FACES (tests): momentum sweeps read the stored west-flux plane in every row
+    bool sweep2 = true;           // SRCFD_SLAB_SWEEP2=0: momentum sweeps one per launch (k_slab_sweep) instead of two per pass
+    double* sweep2_partials = nullptr;   // [units][2] partial sums of k_slab_sweep2
+    int sweep2_slots[2] = {0, 0}; // resident warps of k_slab_sweep2<upwind / QUICK> on this device
+    int sweep2_chunks = 0;        // SRCFD_SWEEP2_CHUNKS (experiments): row chunks per strip, 0 = one unit per resident warp
+    int64_t sweep2_passes = 0;
     long long warp_steps = 0;     // of the running solve
     int64_t tile_solves = 0, stream_solves = 0;
 };
@@ -47,7 +52,7 @@ static void slab_release(srcfd_handle* h) {
     if (!S) return;
     for (int q = 0; q < SLAB_MAX_WORLD; ++q)
         if (S->peer_ipc[q] && S->peer_base[q]) cudaIpcCloseMemHandle(S->peer_base[q]);
-    cudaFree(S->mail); cudaFree(S->sc); cudaFree(S->sums); cudaFree(S->sweep_partials); cudaFree(S->tickets);
+    cudaFree(S->mail); cudaFree(S->sc); cudaFree(S->sums); cudaFree(S->sweep_partials); cudaFree(S->sweep2_partials); cudaFree(S->tickets);
     if (S->sc_host) cudaFreeHost(S->sc_host);
     delete S;
     h->slab = nullptr;
@@ -197,17 +202,38 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         }
     } else {
         SolveArgs a = slab_solve_args(h, k, k);
-        for (int t = 0; t < nsw; ++t) {
+        const bool paired = h->ff_paired && !S->four_faces;   // the library's own fluxes (k_slab_sweep)
+        // two sweeps per pass over HBM (k_slab_sweep2); an odd sweep left over runs alone.  One warp per (strip of 32 columns
+        // of which it owns 32-2NB, chunk of rows), about one unit per resident warp, chunks of at least 32 rows.
+        const int NBv = op == OP_QUICK ? 2 : 1, wv = 32 - 2 * NBv;
+        const int strips = (h->K.ny + wv - 1) / wv;
+        const int slots = S->sweep2_slots[op == OP_QUICK ? 1 : 0];
+        int nchunks = std::max(1, std::min(slots / strips, h->K.nx / 32));
+        if (S->sweep2_chunks > 0) nchunks = std::min(S->sweep2_chunks, std::max(1, h->K.nx / 32));
+        const int RB = (h->K.nx + nchunks - 1) / nchunks;
+        nchunks = (h->K.nx + RB - 1) / RB;
+        const int units = strips * nchunks;
+        for (int t = 0; t < nsw;) {
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
-            const int gx = (h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS;
-            const dim3 grid(gx, std::max(1, std::min(h->K.nx, (h->num_sms * 8 + gx - 1) / gx)));
+            const bool two = S->sweep2 && slots > 0 && nsw - t >= 2;
+            if (two) {
+                const int grid2 = (units + SLAB_THREADS / 32 - 1) / (SLAB_THREADS / 32);
+#define SLAB_SWEEP2(OPv, Pv) k_slab_sweep2<OPv, Pv><<<grid2, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, RB, strips, units, S->sweep2_partials, S->sums + t, S->tickets + 1, done)
+                if (op == OP_UPWIND) { if (paired) SLAB_SWEEP2(OP_UPWIND, true); else SLAB_SWEEP2(OP_UPWIND, false); }
+                else { if (paired) SLAB_SWEEP2(OP_QUICK, true); else SLAB_SWEEP2(OP_QUICK, false); }
+#undef SLAB_SWEEP2
+                S->sweep2_passes += 1;
+            } else {
+                const int gx = (h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS;
+                const dim3 grid(gx, std::max(1, std::min(h->K.nx, (h->num_sms * 8 + gx - 1) / gx)));
 #define SLAB_SWEEP(OPv, Pv) k_slab_sweep<OPv, Pv><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done)
-            const bool paired = h->ff_paired && !S->four_faces;   // the library's own fluxes (k_slab_sweep)
-            if (op == OP_UPWIND) { if (paired) SLAB_SWEEP(OP_UPWIND, true); else SLAB_SWEEP(OP_UPWIND, false); }
-            else { if (paired) SLAB_SWEEP(OP_QUICK, true); else SLAB_SWEEP(OP_QUICK, false); }
+                if (op == OP_UPWIND) { if (paired) SLAB_SWEEP(OP_UPWIND, true); else SLAB_SWEEP(OP_UPWIND, false); }
+                else { if (paired) SLAB_SWEEP(OP_QUICK, true); else SLAB_SWEEP(OP_QUICK, false); }
 #undef SLAB_SWEEP
+            }
             LAUNCH_CHECK(h);
+            t += two ? 2 : 1;
             src = dst; dst = (dst == o1) ? o2 : o1;
         }
     }
@@ -411,6 +437,17 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     CKS(cudaMalloc(&S->sums, sizeof(double) * SLAB_NS));
     CKS(cudaMemsetAsync(S->sums, 0, sizeof(double) * SLAB_NS, h->stream));
     CKS(cudaMalloc(&S->sweep_partials, sizeof(double) * ((size_t)((h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS) * h->K.nx + 1)));
+    if (const char* e = getenv("SRCFD_SLAB_SWEEP2")) S->sweep2 = atoi(e) != 0;
+    if (const char* e = getenv("SRCFD_SWEEP2_CHUNKS")) S->sweep2_chunks = atoi(e);
+    {   // k_slab_sweep2: resident warps per device (unit count of a pass) and room for two partial sums per unit
+        int occ_u = 0, occ_q = 0;
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_slab_sweep2<OP_UPWIND, true>, SLAB_THREADS, 0));
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_slab_sweep2<OP_QUICK, true>, SLAB_THREADS, 0));
+        S->sweep2_slots[0] = h->num_sms * occ_u * (SLAB_THREADS / 32);
+        S->sweep2_slots[1] = h->num_sms * occ_q * (SLAB_THREADS / 32);
+        const size_t units_max = (size_t)((h->K.ny + 27) / 28) * (size_t)(h->K.nx / 32 + 1);
+        CKS(cudaMalloc(&S->sweep2_partials, sizeof(double) * 2 * units_max));
+    }
     CKS(cudaMalloc(&S->tickets, sizeof(unsigned) * 4));
     CKS(cudaMemsetAsync(S->tickets, 0, sizeof(unsigned) * 4, h->stream));
     CKS(cudaStreamSynchronize(h->stream));

@@ -124,9 +124,18 @@ def test_slab_pressure_rest_and_denormal_fields(world, pressure_kernel):
         _close(slabs)
 
 
+@pytest.fixture(params=["two_per_pass", "one_per_launch"])
+def momentum_kernel(request, monkeypatch):
+    """The momentum sweeps of the slab path: two sweeps per pass over HBM (k_slab_sweep2, the default; an odd sweep left
+    over runs alone) and one sweep per launch (k_slab_sweep)."""
+    monkeypatch.delenv("SRCFD_SWEEP2_CHUNKS", raising=False)
+    monkeypatch.setenv("SRCFD_SLAB_SWEEP2", "1" if request.param == "two_per_pass" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
-def test_slab_momentum_matches_oracle(world, scheme):
+def test_slab_momentum_matches_oracle(world, scheme, momentum_kernel):
     from srcfd import slab, _capi as capi
     nx, ny = 96, 50
     rng = np.random.default_rng(2)
@@ -149,9 +158,48 @@ def test_slab_momentum_matches_oracle(world, scheme):
             _close(slabs)
 
 
+@pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
+def test_slab_momentum_two_per_pass_many_strips_and_chunks(scheme, monkeypatch):
+    """k_slab_sweep2 on a plane of several column strips and row chunks (ragged last strip and last chunk, chunk counts
+    forced through SRCFD_SWEEP2_CHUNKS as well), even and odd sweep counts, a tolerance met inside a block (replay), on
+    uploaded fluxes with NON-zero boundary-face fluxes, so that QUICK's out-of-plane second neighbours (hazard H4) are
+    used at both levels of a pass: fields and sweep counts equal to the oracle's, sums equal to the one-sweep kernel's."""
+    from srcfd import slab, _capi as capi
+    nx, ny = 203, 131
+    rng = np.random.default_rng(12)
+    Var = rng.uniform(-1, 1, (3, nx + 2, ny + 2)); VarOld = Var + 0.01 * rng.uniform(-1, 1, Var.shape)
+    Ff = 0.002 * rng.uniform(-1, 1, (4, nx + 2, ny + 2))
+    fn = O.solve_momentum_quick if scheme == "QUICK" else O.solve_momentum_upwind
+    sc = capi.SCHEME_QUICK if scheme == "QUICK" else capi.SCHEME_UPWIND
+    for chunks in ("", "1", "5"):
+        monkeypatch.setenv("SRCFD_SLAB_SWEEP2", "1")
+        if chunks:
+            monkeypatch.setenv("SRCFD_SWEEP2_CHUNKS", chunks)
+        else:
+            monkeypatch.delenv("SRCFD_SWEEP2_CHUNKS", raising=False)
+        for tol, cap, k in ((0.0, 6, 0), (0.0, 7, 1), (1e-30, 1, 0), (None, 30, 1)):
+            if tol is None:                                   # a tolerance the 4th sweep meets: overshoot and replay
+                B = Var.copy()
+                _, hist = fn(B, VarOld, Ff, k, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0 / 100.0, (1.0 / nx) * (1.0 / ny), order=O.ORDER_JACOBI,
+                             tolerance=0.0, max_iter=6, rms_hist=True)
+                tol = 0.5 * (hist[2] + hist[3])
+                assert hist[3] < tol < hist[2]
+            case = O.Case(nx=nx, ny=ny, Re=100.0, dt=1e-3, scheme=scheme, inner_tol=tol, inner_max=cap, order=O.ORDER_JACOBI)
+            slabs = _make(case, 1, 12, Var=Var, VarOld=VarOld, Ff=Ff)
+            n, rms = slab.solve_momentum(slabs, k, sc)
+            B = Var.copy()
+            m, hist = fn(B, VarOld, Ff, k, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0 / 100.0, (1.0 / nx) * (1.0 / ny), order=O.ORDER_JACOBI,
+                         tolerance=tol, max_iter=cap, rms_hist=True)
+            got = _gather(slabs)[0]
+            assert n == m, (scheme, chunks, tol, cap, k, n, m)
+            assert np.array_equal(got[k], B[k, 1:-1]), (scheme, chunks, tol, cap, k, np.max(np.abs(got[k] - B[k, 1:-1])))
+            assert abs(rms - hist[-1]) <= 1e-12 * abs(hist[-1]), (rms, hist[-1])
+            _close(slabs)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("scheme", ["UPWIND", "QUICK"])
-def test_slab_momentum_with_library_fluxes(world, scheme, monkeypatch):
+def test_slab_momentum_with_library_fluxes(world, scheme, monkeypatch, momentum_kernel):
     """Momentum solves on face fluxes as the library's own kernels leave them (BCs, linear_interpolation, update_flux on
     every slab's local rows, halo rows included) instead of uploaded ones: the slabs' fluxes equal the undivided ones,
     the W/S planes are the negated E/N planes of the neighbouring cell -- which lets the sweep take the
