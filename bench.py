@@ -304,7 +304,8 @@ def large_grid_record(device):
         ms = s.h.timer_stop()
         lups = float(n) * n * sw
         ach = BYTES_PER_LUP_MOMENTUM * lups / (ms * 1e-3) / 1e9
-        two = os.environ.get("SRCFD_SLAB_SWEEP2", "1") != "0"
+        e = os.environ.get("SRCFD_SLAB_SWEEP2")                # library default: two sweeps per pass for upwind, one per launch for QUICK
+        two = (not scheme) if e is None else (e != "0")
         kern = (f"k_slab_sweep2<{name}, paired fluxes> (two JACOBI sweeps per pass over HBM: register windows per warp, the west flux is the "
                 "east flux of the row above; 24 B of DRAM traffic per cell update against 40 algorithmic)") if two else \
                (f"k_slab_sweep<{name}, paired fluxes> (one JACOBI sweep per launch; the west flux is the east flux of the "

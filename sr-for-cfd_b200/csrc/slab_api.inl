@@ -38,9 +38,12 @@ struct SlabState {
     bool use_tiles = true;
     bool force_stream = false;    // SRCFD_JTB2_FORCE (experiments): streaming kernel on thin slabs too
     bool four_faces = false;      // SRCFD_SLAB_FOUR_FACES (tests): momentum sweeps read the stored west-flux plane in every row
-    bool sweep2 = true;           // SRCFD_SLAB_SWEEP2=0: momentum sweeps one per launch (k_slab_sweep) instead of two per pass
+    int sweep2 = 1;               // momentum sweeps two per pass over HBM (k_slab_sweep2): bit 0 upwind, bit 1 QUICK.  Default: upwind
+                                  // only (4096^2: 115 against 92 GLUP/s; QUICK 72 against 87: its 5-row windows, 14 % strip overlap and
+                                  // spills cost more than the saved traffic).  SRCFD_SLAB_SWEEP2=0 none, =1 both
     double* sweep2_partials = nullptr;   // [units][2] partial sums of k_slab_sweep2
     int sweep2_slots[2] = {0, 0}; // resident warps of k_slab_sweep2<upwind / QUICK> on this device
+    int sweep2_pf = 3;            // SRCFD_SWEEP2_PF: rows ahead that k_slab_sweep2 prefetches into L2 (0 = off; 4096^2 upwind: 109 GLUP/s off, 121 at 2-4, 113 at 12)
     int sweep2_chunks = 0;        // SRCFD_SWEEP2_CHUNKS (experiments): row chunks per strip, 0 = one unit per resident warp
     int64_t sweep2_passes = 0;
     long long warp_steps = 0;     // of the running solve
@@ -216,10 +219,10 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
         for (int t = 0; t < nsw;) {
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
-            const bool two = S->sweep2 && slots > 0 && nsw - t >= 2;
+            const bool two = (S->sweep2 & (op == OP_QUICK ? 2 : 1)) && slots > 0 && nsw - t >= 2;
             if (two) {
-                const int grid2 = (units + SLAB_THREADS / 32 - 1) / (SLAB_THREADS / 32);
-#define SLAB_SWEEP2(OPv, Pv) k_slab_sweep2<OPv, Pv><<<grid2, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, RB, strips, units, S->sweep2_partials, S->sums + t, S->tickets + 1, done)
+                const int grid2 = (units + SW2_THREADS / 32 - 1) / (SW2_THREADS / 32);
+#define SLAB_SWEEP2(OPv, Pv) k_slab_sweep2<OPv, Pv><<<grid2, SW2_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, RB, strips, units, S->sweep2_pf, S->sweep2_partials, S->sums + t, S->tickets + 1, done)
                 if (op == OP_UPWIND) { if (paired) SLAB_SWEEP2(OP_UPWIND, true); else SLAB_SWEEP2(OP_UPWIND, false); }
                 else { if (paired) SLAB_SWEEP2(OP_QUICK, true); else SLAB_SWEEP2(OP_QUICK, false); }
 #undef SLAB_SWEEP2
@@ -437,14 +440,15 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     CKS(cudaMalloc(&S->sums, sizeof(double) * SLAB_NS));
     CKS(cudaMemsetAsync(S->sums, 0, sizeof(double) * SLAB_NS, h->stream));
     CKS(cudaMalloc(&S->sweep_partials, sizeof(double) * ((size_t)((h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS) * h->K.nx + 1)));
-    if (const char* e = getenv("SRCFD_SLAB_SWEEP2")) S->sweep2 = atoi(e) != 0;
+    if (const char* e = getenv("SRCFD_SLAB_SWEEP2")) S->sweep2 = atoi(e) != 0 ? 3 : 0;
     if (const char* e = getenv("SRCFD_SWEEP2_CHUNKS")) S->sweep2_chunks = atoi(e);
+    if (const char* e = getenv("SRCFD_SWEEP2_PF")) S->sweep2_pf = std::max(0, atoi(e));
     {   // k_slab_sweep2: resident warps per device (unit count of a pass) and room for two partial sums per unit
         int occ_u = 0, occ_q = 0;
-        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_slab_sweep2<OP_UPWIND, true>, SLAB_THREADS, 0));
-        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_slab_sweep2<OP_QUICK, true>, SLAB_THREADS, 0));
-        S->sweep2_slots[0] = h->num_sms * occ_u * (SLAB_THREADS / 32);
-        S->sweep2_slots[1] = h->num_sms * occ_q * (SLAB_THREADS / 32);
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_slab_sweep2<OP_UPWIND, true>, SW2_THREADS, 0));
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_slab_sweep2<OP_QUICK, true>, SW2_THREADS, 0));
+        S->sweep2_slots[0] = h->num_sms * occ_u * (SW2_THREADS / 32);
+        S->sweep2_slots[1] = h->num_sms * occ_q * (SW2_THREADS / 32);
         const size_t units_max = (size_t)((h->K.ny + 27) / 28) * (size_t)(h->K.nx / 32 + 1);
         CKS(cudaMalloc(&S->sweep2_partials, sizeof(double) * 2 * units_max));
     }

@@ -15,9 +15,11 @@ variants = [("two_per_pass", {"SRCFD_SLAB_SWEEP2": "1"}), ("one_per_launch", {"S
 for ch in os.environ.get("PROBE_CHUNKS", "8,12,24,34,64").split(","):
     if ch:
         variants.append((f"two_per_pass_chunks{ch}", {"SRCFD_SLAB_SWEEP2": "1", "SRCFD_SWEEP2_CHUNKS": ch}))
-fields = None
+for pf in os.environ.get("PROBE_PF", "").split(","):
+    if pf:
+        variants.append((f"two_per_pass_pf{pf}", {"SRCFD_SLAB_SWEEP2": "1", "SRCFD_SWEEP2_PF": pf}))
 for vname, env in variants:
-  for key in ("SRCFD_SLAB_SWEEP2", "SRCFD_SWEEP2_CHUNKS"):
+  for key in ("SRCFD_SLAB_SWEEP2", "SRCFD_SWEEP2_CHUNKS", "SRCFD_SWEEP2_PF"):
       os.environ.pop(key, None)
   os.environ.update(env)
   for scheme, name in ((False, "upwind"), (True, "quick")):
