@@ -242,7 +242,9 @@ int srcfd_sr_decode_device(srcfd_sr *h, uint64_t z_dev, int B, uint64_t out_dev,
  * 2 = as 1 with the final conv on the CUDA-core tile kernel (what the tensor-core final conv is tested against),
  * 3 = split-operand tensor cores: fp32 activations, every product as three bf16 MMAs (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi),
  *     fp32 epilogues and final conv -- the accuracy of the fp32 path (1e-4 against the restatement) at tensor-core speed;
- *     THE DEFAULT of a new srcfd_sr context */
+ *     THE DEFAULT of a new srcfd_sr context; its last two layers (ConvT 16 -> 8 and the final 3x3 conv, sr-ae-conv.ipynb
+ *     cell 277-287) run as ONE kernel that keeps the 400x400x8 activation between them in shared memory;
+ * 4 = as 3 with those two layers as separate launches (same bits; parity tests) */
 int srcfd_sr_set_precision(srcfd_sr *h, int mode);
 int srcfd_sr_tc_error(srcfd_sr *h, int *flag);
 /* one tensor-core ConvT layer (1..4) in isolation, host fp32 in/out (operands rounded to bf16): parity tests */

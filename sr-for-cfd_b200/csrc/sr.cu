@@ -262,6 +262,8 @@ struct srcfd_sr {
     // environment knobs, read once at creation
     int tc_persist = 16;               // SRCFD_TC_PERSIST: CTAs per SM of the persistent ConvT launch (batch 1024: 8.37 ms with one
                                        // tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM)
+    int tail_fused = 1;                // SRCFD_TAIL_FUSED=0: split-operand path with the last ConvT and the final conv as two launches
+    int tail_fused_default = 1;
     int final_tc = 1;                  // SRCFD_FINAL_TC=0: final conv on the CUDA-core tile kernel
     int final_tc_rows = 8;             // SRCFD_FINAL_TC_ROWS: 4 | 8 | 16 output rows per CTA of the tensor-core final conv
     double* stats_dev = nullptr;       // per-field {mean_lr, std_lr, mean_hr, std_hr} of srcfd_sr_super_resolve
@@ -393,9 +395,22 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         if (int rc = launch_convT_tc3<128, 256>(h, h->act[1], h->dec[2], h->act[2], B, 25)) return rc;
         if (int rc = launch_convT_tc3<64, 128>(h, h->act[2], h->dec[3], h->act[3], B, 50)) return rc;
         if (int rc = launch_convT_tc3<32, 64>(h, h->act[3], h->dec[4], h->act[4], B, 100)) return rc;
-        if (int rc = launch_convT_tc3<16, 32>(h, h->act[4], h->dec[5], h->act[5], B, 200)) return rc;
-        k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->fcw, out_dev, B, 400, 400);
-        h->launches += 1;
+        if (h->tail_fused) {
+            // last ConvT + final conv in one kernel: the (B, 400, 400, 8) activation between them stays in shared memory
+            srtc::FinalW fw;
+            memcpy(fw.w, h->fcw.w, sizeof(fw.w)); fw.b = h->fcw.b;
+            const size_t smem = srtc::tail_fused_smem();
+            static bool attr_done[64] = {false};
+            if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_tail_fused_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
+            const unsigned np = (200 + srtc::TF_OWN - 1) / srtc::TF_OWN;
+            srtc::k_tail_fused_tc3<<<dim3(np, np, B), 128, smem, h->stream>>>(h->act[4], h->dec[5].Wbf, h->dec[5].Wlo, h->dec[5].b, fw, out_dev, 200, 200, h->tc_err);
+            h->launches += 1;
+            SRCK(cudaGetLastError());
+        } else {
+            if (int rc = launch_convT_tc3<16, 32>(h, h->act[4], h->dec[5], h->act[5], B, 200)) return rc;
+            k_conv3x3_c8_final<float><<<dim3((400 + FC_TX - 1) / FC_TX, (400 + FC_TY - 1) / FC_TY, B), 256, 0, h->stream>>>(h->act[5], h->fcw, out_dev, B, 400, 400);
+            h->launches += 1;
+        }
     } else {
         // ConvT1 (3x3, stride 2: overlapping taps): tensor-core GEMM per tap into Y (act[5] reused as fp32 scratch,
         // B*144 x 1152), then col2im + bias + swish -> bf16 activation
@@ -447,6 +462,7 @@ int srcfd_sr_create(int device, srcfd_sr** out) {
     SRCK(cudaEventCreate(&h->ea)); SRCK(cudaEventCreate(&h->eb));
     if (const char* e = getenv("SRCFD_TC_PERSIST")) h->tc_persist = atoi(e);
     if (const char* e = getenv("SRCFD_FINAL_TC")) h->final_tc = atoi(e);
+    if (const char* e = getenv("SRCFD_TAIL_FUSED")) h->tail_fused = h->tail_fused_default = atoi(e);
     if (const char* e = getenv("SRCFD_FINAL_TC_ROWS")) h->final_tc_rows = atoi(e);
     *out = h;
     return SRCFD_OK;
@@ -612,8 +628,10 @@ int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev,
 }
 // 0 = fp32 CUDA cores (default, parity path); 1 = bf16 tcgen05 tensor cores for the four 2x2/stride-2 ConvT layers
 int srcfd_sr_set_precision(srcfd_sr* h, int mode) {
-    if (!h || mode < 0 || mode > 3) return sr_fail(SRCFD_ERR_ARG, "bad argument");
-    h->precision = mode == 0 ? 0 : mode == 3 ? 3 : 1;
+    if (!h || mode < 0 || mode > 4) return sr_fail(SRCFD_ERR_ARG, "bad argument");
+    h->precision = mode == 0 ? 0 : mode >= 3 ? 3 : 1;
+    if (mode == 3) h->tail_fused = h->tail_fused_default; // mode 4: split-operand path with the last ConvT and the final conv as two launches (parity tests)
+    if (mode == 4) h->tail_fused = 0;
     if (mode == 1) h->final_tc = 1;        // mode 2: bf16 layers with the final conv on the CUDA-core tile kernel (parity tests)
     if (mode == 2) h->final_tc = 0;
     return SRCFD_OK;

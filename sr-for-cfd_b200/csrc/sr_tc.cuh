@@ -186,7 +186,15 @@ constexpr size_t convT_tc_smem() { return (size_t)(128 + ND) * KD * 2; }
 // KPART > 1 stages the A tile in K-parts (the 3x3 layer: K = 256 would need 256 KB for both operands' two halves); the
 // weights stay resident.  Same tile / descriptor / epilogue structure as k_convT2x2_tc.
 // expf + approximate division (MUFU.EX2, MUFU.RCP: ~2 ulp each) -- three orders of magnitude inside the 1e-4 bar of this path
-__device__ __forceinline__ float swish_exact(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// (round 2: ex2.approx.ftz / rcp.approx.ftz spelled out -- __expf / __fdividef wrap the same two MUFU operations in denormal and
+// range fix-ups, 13.7 instructions per value in the fused tail's epilogue against 5 here; flushing matters only for |x| > 87,
+// where the result is 0 or x to well inside the bar)
+__device__ __forceinline__ float swish_exact(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     __nv_bfloat162 h[4], l[4];
 #pragma unroll
@@ -502,6 +510,182 @@ __global__ void __launch_bounds__(128) k_conv3x3_c8_final_tc(const __nv_bfloat16
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOL) : "memory");
+}
+
+// ---- fused tail of the split-operand decoder (round 2): ConvT(16 -> 8, 2x2, stride 2) + swish + Conv(8 -> 1, 3x3, 'same') ----
+// (sr-ae-conv.ipynb cell 277-287: the last two layers of decoder_400.)  Unfused, the (B, 400, 400, 8) fp32 activation between
+// them is written and read back once: 1.3 GB per 128 samples, more than every other tensor of the decoder together.  Here a
+// CTA takes a patch of 16 x 16 pixels of the (B, 200, 200, 16) input -- two 128-row tiles of the same implicit GEMM as
+// k_convT2x2_tc3<16, 32> (three bf16 MMAs per tile into a 32-column fp32 TMEM accumulator each) --, its epilogue (bias, expf
+// swish) writes the 32 x 32 x 8 activation tile to SHARED memory (zeros where the input pixel lies outside the image: the
+// final conv's 'same' padding), and the final conv runs from there on the CUDA cores: the middle 28 x 28 output pixels, the
+// ring of one input pixel around the owned 14 x 14 being the conv's halo (recomputed by the neighbouring patches:
+// (16/14)^2 = 1.31x the ConvT work and input reads).  Same operands, MMA order, swish and FMA order as the two kernels it
+// replaces, so the output is the same bits.
+constexpr int TF_P = 16, TF_OWN = TF_P - 2, TF_AT = 2 * TF_P;
+constexpr size_t TF_ACT_BYTES = (size_t)TF_AT * TF_AT * 8 * 4, TF_ATILE = 128 * 16 * 2, TF_B_BYTES = 32 * 16 * 2;
+constexpr size_t tail_fused_smem() { return TF_ACT_BYTES + 2 * TF_B_BYTES; }   // (the A operand lives inside the activation tile's space)
+// 16-byte chunk of channel half h (0: c0-3, 1: c4-7) of pixel (row, col) in the activation tile.  The epilogue's lanes write
+// pixel PAIRS 64 B apart and the conv's lanes read consecutive pixels; the XOR keeps both free of bank conflicts.
+__device__ __forceinline__ int tf_chunk(int row, int col, int h) {
+    const int pp = col >> 1, q = ((col & 1) << 1) | h;
+    return (row * TF_AT + 2 * pp) * 2 + (q ^ ((pp >> 1) & 3));
+}
+
+__global__ void __launch_bounds__(128) k_tail_fused_tc3(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Whi,
+                                                         const __nv_bfloat16* __restrict__ Wlo, const float* __restrict__ bias,
+                                                         const FinalW fw, float* __restrict__ out, int H, int Wd, int* err) {
+    constexpr int KD = 16, ND = 32, MT = 128, KC = KD / 8;
+    constexpr uint32_t LBO_A = (MT / 8) * 128, LBO_B = (ND / 8) * 128, SBO = 128;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* act = reinterpret_cast<float*>(smem_raw);          // [32][32][8] fp32
+    unsigned char* sAh = smem_raw;                            // two tiles of 128 rows, canonical K-major layout: dead once the MMAs
+    unsigned char* sAl = sAh + 2 * TF_ATILE;                  // have completed, i.e. before the first activation is written over them
+    unsigned char* sBh = smem_raw + TF_ACT_BYTES;
+    unsigned char* sBl = sBh + TF_B_BYTES;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, y0 = (int)blockIdx.y * TF_OWN - 1, x0 = (int)blockIdx.x * TF_OWN - 1;   // input pixel of patch (0, 0)
+    if (tid < 8) s_bias[tid] = bias[tid];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- the A patch: 256 rows x 2 chunks of 8 floats, every load in flight before the first split
+    const float* Ab = A + (long long)b * H * Wd * KD;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = tid + q * 128, r = c >> 1, kc = c & 1;
+        const int Y = y0 + (r >> 4), X = x0 + (r & 15);
+        va[q] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q] = va[q];
+        if (Y >= 0 && Y < H && X >= 0 && X < Wd) {
+            const float4* src = reinterpret_cast<const float4*>(Ab + ((long long)Y * Wd + X) * KD + kc * 8);
+            va[q] = __ldg(src); vb[q] = __ldg(src + 1);
+        }
+    }
+    for (int c = tid; c < ND * KC; c += 128) {                // both halves of the (32 x 16) weights
+        const int n = c / KC, kc = c - n * KC;
+        const size_t so = (size_t)kc * LBO_B + (n >> 3) * SBO + (n & 7) * 16;
+        *reinterpret_cast<uint4*>(sBh + so) = *reinterpret_cast<const uint4*>(Whi + (size_t)n * KD + kc * 8);
+        *reinterpret_cast<uint4*>(sBl + so) = *reinterpret_cast<const uint4*>(Wlo + (size_t)n * KD + kc * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = tid + q * 128, r = c >> 1, kc = c & 1, t = r >> 7, rr = r & 127;
+        const float v[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const size_t so = (size_t)t * TF_ATILE + (size_t)kc * LBO_A + (rr >> 3) * SBO + (rr & 7) * 16;
+        *reinterpret_cast<uint4*>(sAh + so) = hi;
+        *reinterpret_cast<uint4*>(sAl + so) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(MT, ND);
+        const uint32_t ah = smem_u32(sAh), al = smem_u32(sAl), bh = smem_u32(sBh), bl = smem_u32(sBl);
+        const uint64_t bdh = make_smem_desc(bh, LBO_B, SBO), bdl = make_smem_desc(bl, LBO_B, SBO);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                          // K = 16: one K-step per tile
+            const uint64_t adh = make_smem_desc(ah + (uint32_t)(t * TF_ATILE), LBO_A, SBO), adl = make_smem_desc(al + (uint32_t)(t * TF_ATILE), LBO_A, SBO);
+            umma_bf16(tmem + (uint32_t)(t * ND), adh, bdh, idesc, 0u);
+            umma_bf16(tmem + (uint32_t)(t * ND), adh, bdl, idesc, 1u);
+            umma_bf16(tmem + (uint32_t)(t * ND), adl, bdh, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    bool dead = false;
+    {                                                          // bounded wait: never hang the GPU
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        }
+        if (!done) { if (lane == 0) atomicExch(err, 1); dead = true; }
+    }
+    dead = __syncthreads_or(dead ? 1 : 0) != 0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!dead) {
+        // ---- ConvT epilogue: thread = accumulator row of both tiles; bias + swish into the shared activation tile
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = t * MT + warp * 32 + lane, py = r >> 4, px = r & 15;
+            const int Y = y0 + py, X = x0 + px;
+            const bool inside = Y >= 0 && Y < H && X >= 0 && X < Wd;
+#pragma unroll
+            for (int c0 = 0; c0 < ND; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * ND + c0);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 16; g += 8) {
+                    const int tap = (c0 + g) >> 3, dy = tap >> 1, dx = tap & 1;
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_bias), b1 = *reinterpret_cast<const float4*>(s_bias + 4);
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                    if (inside) {
+                        o0 = make_float4(swish_exact(__uint_as_float(v[g + 0]) + b0.x), swish_exact(__uint_as_float(v[g + 1]) + b0.y),
+                                         swish_exact(__uint_as_float(v[g + 2]) + b0.z), swish_exact(__uint_as_float(v[g + 3]) + b0.w));
+                        o1 = make_float4(swish_exact(__uint_as_float(v[g + 4]) + b1.x), swish_exact(__uint_as_float(v[g + 5]) + b1.y),
+                                         swish_exact(__uint_as_float(v[g + 6]) + b1.z), swish_exact(__uint_as_float(v[g + 7]) + b1.w));
+                    }
+                    float4* at = reinterpret_cast<float4*>(act);
+                    at[tf_chunk(2 * py + dy, 2 * px + dx, 0)] = o0;
+                    at[tf_chunk(2 * py + dy, 2 * px + dx, 1)] = o1;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64) : "memory");
+    if (dead) return;
+    // ---- final conv on the middle 28 x 28 pixels of the tile: thread = column, 7 rows each (k_conv3x3_c8_final's FMA order)
+    const int tx = lane, tq = warp;
+    if (tx < 2 * TF_OWN) {
+        const float bs = fw.b;
+        float acc[7] = {bs, bs, bs, bs, bs, bs, bs};
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {                          // tile rows 7*tq + 1 + r feed outputs r-2 .. r
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4* at = reinterpret_cast<const float4*>(act);
+                const float4 a = at[tf_chunk(7 * tq + 1 + r, tx + 1 + kx, 0)], c4 = at[tf_chunk(7 * tq + 1 + r, tx + 1 + kx, 1)];
+                const float xv[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int o = 0; o < 7; ++o) {
+                    const int ky = r - o;
+                    if (ky >= 0 && ky < 3) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[o] = fmaf(xv[c], fw.w[(ky * 3 + kx) * 8 + c], acc[o]);
+                    }
+                }
+            }
+        }
+        const int OH = 2 * H, OW = 2 * Wd;
+        const int gx = 2 * (int)blockIdx.x * TF_OWN + tx;
+        if (gx < OW) {
+#pragma unroll
+            for (int o = 0; o < 7; ++o) {
+                const int gy = 2 * (int)blockIdx.y * TF_OWN + 7 * tq + o;
+                if (gy < OH) out[((long long)b * OH + gy) * OW + gx] = acc[o];
+            }
+        }
+    }
 }
 
 }  // namespace srtc

@@ -211,8 +211,9 @@ def launch_count(device=None) -> int:
 
 def set_precision(mode: str = "bf16x3", device=None):
     """'fp32' (CUDA cores), 'bf16x3' (tcgen05, split operands: fp32-grade accuracy), 'bf16' (tcgen05, bf16 operands and
-    activations: fastest, ~3e-2 of the output range), 'bf16_cc_final' (as bf16 with the CUDA-core final conv; tests)."""
-    _sr_check(capi.lib().srcfd_sr_set_precision(_context(device)["h"], C.c_int({"fp32": 0, "bf16": 1, "bf16_cc_final": 2, "bf16x3": 3}[mode])))
+    activations: fastest, ~3e-2 of the output range), 'bf16_cc_final' (as bf16 with the CUDA-core final conv; tests),
+    'bf16x3_unfused' (as bf16x3 with the last ConvT and the final conv as two launches instead of the fused tail; tests)."""
+    _sr_check(capi.lib().srcfd_sr_set_precision(_context(device)["h"], C.c_int({"fp32": 0, "bf16": 1, "bf16_cc_final": 2, "bf16x3": 3, "bf16x3_unfused": 4}[mode])))
 
 
 def tc_error(device=None) -> bool:

@@ -124,6 +124,26 @@ def test_final_conv_on_tensor_cores_matches_cuda_core_kernel():
         assert err[sl].max() <= 4e-3 * scale
 
 
+@pytest.mark.parametrize("B", [1, 5, 130])
+def test_fused_decoder_tail_equals_the_two_launches(B):
+    """Split-operand path: the fused tail (last ConvT + swish + final 3x3 conv in one kernel, the 400x400x8 activation in
+    shared memory; patches of 14x14 input pixels, ragged at the right/bottom edge, zero padding at every image border)
+    against the same two layers as separate launches: same operands, MMA order and FMA order, hence the same bits."""
+    from srcfd import sr
+    dec = sr.synthetic_decoder(0)
+    z = np.random.default_rng(100 + B).standard_normal((B, 50)).astype(np.float32)
+    try:
+        sr.set_precision("bf16x3_unfused")
+        ref = dec.predict(z)
+        sr.set_precision("bf16x3")
+        out = dec.predict(z)
+    finally:
+        sr.set_precision("bf16x3")
+    assert not sr.tc_error()
+    assert np.array_equal(out, ref), (np.abs(out - ref).max(), np.unravel_index(np.abs(out - ref).argmax(), out.shape))
+    assert np.abs(ref).max() > 1e-3
+
+
 def test_super_resolve_device_pipeline(golden_dir):
     """srcfd_sr_super_resolve: statistics blend, standardisation, inverse standardisation and the NaN/Inf guard on the
     device, many fields per call -- against the reference's host statements around the same (GPU) networks."""

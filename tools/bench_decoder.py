@@ -16,7 +16,7 @@ z = torch.randn(B, 50, device="cuda", dtype=torch.float32, generator=torch.Gener
 out = torch.empty(B, 400, 400, 1, device="cuda", dtype=torch.float32)
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 res = {}
-for mode in ("fp32", "bf16x3", "bf16"):
+for mode in ("fp32", "bf16x3_unfused", "bf16x3", "bf16"):
     sr.set_precision(mode)
     for _ in range(3):
         sr.decode_device(dec, z.data_ptr(), min(B, 64), out.data_ptr())
