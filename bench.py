@@ -564,8 +564,9 @@ def decoder_record(device, torch):
     return {"metric": "SR decoder inference throughput", "batch": B, "unit": "samples/s",
             "value": res["bf16x3"]["samples_per_s"],
             "value_path": "bf16x3: every ConvT on tcgen05 as three bf16 MMAs per K-step (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi), fp32 activations, "
-                          "epilogues and final conv -- the library's default; held to the fp32 path's tolerance (rtol 1e-4 / atol 5e-5 "
-                          "against the numpy restatement, tests/test_gpu_sr.py)",
+                          "epilogues and final conv; the last ConvT, its swish and the final 3x3 conv are ONE kernel (the 400x400x8 "
+                          "activation between them stays in shared memory) -- the library's default; held to the fp32 path's tolerance "
+                          "(rtol 1e-4 / atol 5e-5 against the numpy restatement, tests/test_gpu_sr.py)",
             "paths": res, "tc_error": bool(sr.tc_error()),
             "bf16_note": "bf16 operands AND activations on tcgen05: within 3e-2 of the output range of the fp32 restatement -- narrower "
                          "arithmetic than the reference's fp32, reported beside the value, not as the value",

@@ -264,6 +264,7 @@ struct srcfd_sr {
                                        // tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM)
     int tail_fused = 1;                // SRCFD_TAIL_FUSED=0: split-operand path with the last ConvT and the final conv as two launches
     int tail_fused_default = 1;
+    int tc3_l1_ctas = 16;              // SRCFD_TC3_L1_CTAS: CTAs per tap of the split-operand 3x3 ConvT (9 taps x 16 = 144 CTAs on 148 SMs)
     int final_tc = 1;                  // SRCFD_FINAL_TC=0: final conv on the CUDA-core tile kernel
     int final_tc_rows = 8;             // SRCFD_FINAL_TC_ROWS: 4 | 8 | 16 output rows per CTA of the tensor-core final conv
     double* stats_dev = nullptr;       // per-field {mean_lr, std_lr, mean_hr, std_hr} of srcfd_sr_super_resolve
@@ -387,7 +388,9 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
             const size_t smem = srtc::convT_tc3_smem<256, 128, 2>();
             static bool attr_done[64] = {false};
             if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<256, 128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
-            srtc::k_convT2x2_tc3<256, 128, 1, 2><<<dim3((unsigned)((M + 127) / 128), 9), 128, smem, h->stream>>>(
+            // CTAs per tap: each stages its tap's 128 KB of split weights once and then walks its share of the 128-row tiles
+            const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((M + 127) / 128, h->tc3_l1_ctas));
+            srtc::k_convT2x2_tc3<256, 128, 1, 2><<<dim3(gx, 9), 128, smem, h->stream>>>(
                 h->act[0], h->dec[1].Wbf, h->dec[1].Wlo, h->dec[1].b, nullptr, M, 12, 12, h->tc_err, h->act[5], 1152);
             srtc::k_col2im_3x3s2_f32<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->act[1], B);
             h->launches += 2;
@@ -463,6 +466,7 @@ int srcfd_sr_create(int device, srcfd_sr** out) {
     if (const char* e = getenv("SRCFD_TC_PERSIST")) h->tc_persist = atoi(e);
     if (const char* e = getenv("SRCFD_FINAL_TC")) h->final_tc = atoi(e);
     if (const char* e = getenv("SRCFD_TAIL_FUSED")) h->tail_fused = h->tail_fused_default = atoi(e);
+    if (const char* e = getenv("SRCFD_TC3_L1_CTAS")) h->tc3_l1_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("SRCFD_FINAL_TC_ROWS")) h->final_tc_rows = atoi(e);
     *out = h;
     return SRCFD_OK;
