@@ -43,6 +43,8 @@ struct SlabState {
                                   // spills cost more than the saved traffic).  SRCFD_SLAB_SWEEP2=0 none, =1 both
     double* sweep2_partials = nullptr;   // [units][2] partial sums of k_slab_sweep2
     int sweep2_slots[2] = {0, 0}; // resident warps of k_slab_sweep2<upwind / QUICK> on this device
+    bool south_from_north = true;  // SRCFD_SLAB_SOUTH_FROM_NORTH=0: the one-sweep kernel streams the stored south-flux plane instead of taking the
+                                  // negated north flux of the cell to the left (library-produced fluxes only; 4096^2: upwind 93.6 -> 98.5, QUICK 87.8 -> 89.9 GLUP/s)
     int sweep2_pf = 3;            // SRCFD_SWEEP2_PF: rows ahead that k_slab_sweep2 prefetches into L2 (0 = off; 4096^2 upwind: 109 GLUP/s off, 121 at 2-4, 113 at 12)
     int sweep2_chunks = 0;        // SRCFD_SWEEP2_CHUNKS (experiments): row chunks per strip, 0 = one unit per resident warp
     int64_t sweep2_passes = 0;
@@ -230,9 +232,10 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
             } else {
                 const int gx = (h->K.ny + SLAB_THREADS - 1) / SLAB_THREADS;
                 const dim3 grid(gx, std::max(1, std::min(h->K.nx, (h->num_sms * 8 + gx - 1) / gx)));
-#define SLAB_SWEEP(OPv, Pv) k_slab_sweep<OPv, Pv><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done)
-                if (op == OP_UPWIND) { if (paired) SLAB_SWEEP(OP_UPWIND, true); else SLAB_SWEEP(OP_UPWIND, false); }
-                else { if (paired) SLAB_SWEEP(OP_QUICK, true); else SLAB_SWEEP(OP_QUICK, false); }
+#define SLAB_SWEEP(OPv, Pv, P2v) k_slab_sweep<OPv, Pv, P2v><<<grid, SLAB_THREADS, 0, h->stream>>>(a, sp, dp, S->own0, S->own1, S->sweep_partials, S->sums + t, S->tickets + 1, done)
+                const bool p2 = paired && S->south_from_north;
+                if (op == OP_UPWIND) { if (p2) SLAB_SWEEP(OP_UPWIND, true, true); else if (paired) SLAB_SWEEP(OP_UPWIND, true, false); else SLAB_SWEEP(OP_UPWIND, false, false); }
+                else { if (p2) SLAB_SWEEP(OP_QUICK, true, true); else if (paired) SLAB_SWEEP(OP_QUICK, true, false); else SLAB_SWEEP(OP_QUICK, false, false); }
 #undef SLAB_SWEEP
             }
             LAUNCH_CHECK(h);
@@ -443,6 +446,7 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     if (const char* e = getenv("SRCFD_SLAB_SWEEP2")) S->sweep2 = atoi(e) != 0 ? 3 : 0;
     if (const char* e = getenv("SRCFD_SWEEP2_CHUNKS")) S->sweep2_chunks = atoi(e);
     if (const char* e = getenv("SRCFD_SWEEP2_PF")) S->sweep2_pf = std::max(0, atoi(e));
+    if (const char* e = getenv("SRCFD_SLAB_SOUTH_FROM_NORTH")) S->south_from_north = atoi(e) != 0;
     {   // k_slab_sweep2: resident warps per device (unit count of a pass) and room for two partial sums per unit
         int occ_u = 0, occ_q = 0;
         CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_slab_sweep2<OP_UPWIND, true>, SW2_THREADS, 0));

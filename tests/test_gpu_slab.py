@@ -229,8 +229,9 @@ def test_slab_momentum_with_library_fluxes(world, scheme, monkeypatch, momentum_
     for k in (0, 1):
         B = V1.copy()
         m = fn(B, VarOld, F1, k, nx, ny, 1.0 / nx, 1.0 / ny, 1e-3, 1.0 / 100.0, (1.0 / nx) * (1.0 / ny), order=O.ORDER_JACOBI, tolerance=0.0, max_iter=9)
-        for four in ("0", "1"):
-            monkeypatch.setenv("SRCFD_SLAB_FOUR_FACES", four)
+        for four in ("0", "1", "w"):                      # both shortcuts / all four stored planes / the west shortcut only
+            monkeypatch.setenv("SRCFD_SLAB_FOUR_FACES", "1" if four == "1" else "0")
+            monkeypatch.setenv("SRCFD_SLAB_SOUTH_FROM_NORTH", "0" if four == "w" else "1")
             slabs = _make(case, world, 12, Var=Var, VarOld=VarOld)
             prepare(slabs)
             if world > 1:

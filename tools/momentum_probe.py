@@ -15,11 +15,13 @@ variants = [("two_per_pass", {"SRCFD_SLAB_SWEEP2": "1"}), ("one_per_launch", {"S
 for ch in os.environ.get("PROBE_CHUNKS", "8,12,24,34,64").split(","):
     if ch:
         variants.append((f"two_per_pass_chunks{ch}", {"SRCFD_SLAB_SWEEP2": "1", "SRCFD_SWEEP2_CHUNKS": ch}))
+if os.environ.get("PROBE_SFN"):
+    variants.append(("one_per_launch_south_from_north", {"SRCFD_SLAB_SWEEP2": "0", "SRCFD_SLAB_SOUTH_FROM_NORTH": "1"}))
 for pf in os.environ.get("PROBE_PF", "").split(","):
     if pf:
         variants.append((f"two_per_pass_pf{pf}", {"SRCFD_SLAB_SWEEP2": "1", "SRCFD_SWEEP2_PF": pf}))
 for vname, env in variants:
-  for key in ("SRCFD_SLAB_SWEEP2", "SRCFD_SWEEP2_CHUNKS", "SRCFD_SWEEP2_PF"):
+  for key in ("SRCFD_SLAB_SWEEP2", "SRCFD_SWEEP2_CHUNKS", "SRCFD_SWEEP2_PF", "SRCFD_SLAB_SOUTH_FROM_NORTH"):
       os.environ.pop(key, None)
   os.environ.update(env)
   for scheme, name in ((False, "upwind"), (True, "quick")):
