@@ -36,6 +36,7 @@ struct SlabState {
     // same bits, small 2-D work units), which counts its own trips to the IEEE routine: the streaming kernel comes
     // back when a tile-kernel solve reports (almost) none.  A handle starts on tiles, i.e. its first solve is the probe.
     bool use_tiles = true;
+    int stream_nl = 4;            // SRCFD_JTB2_NL (experiments): sweeps per pass of the streaming kernel
     bool force_stream = false;    // SRCFD_JTB2_FORCE (experiments): streaming kernel on thin slabs too
     bool four_faces = false;      // SRCFD_SLAB_FOUR_FACES (tests): momentum sweeps read the stored west-flux plane in every row
     int sweep2 = 1;               // momentum sweeps two per pass over HBM (k_slab_sweep2): bit 0 upwind, bit 1 QUICK.  Default: upwind
@@ -189,7 +190,7 @@ static int slab_run_block(srcfd_handle* h, int op, int k, int Sidx, int nsw, int
             const int strips4 = (h->K.ny + 55) / 56, slots = h->num_sms * JTB2_MINB * JTB2_WARPS;
             const bool roomy = S->force_stream || h->K.nx >= 12 * std::max(1, slots / strips4);
             const bool stream = h->jtb_impl == 2 && !S->use_tiles && roomy;
-            int m = std::min(stream ? 4 : h->jtb_H, nsw - t);
+            int m = std::min(stream ? S->stream_nl : h->jtb_H, nsw - t);
             const double* sp = slab_buf(h, k, src);
             double* dp = slab_buf(h, k, dst);
             double* sums = S->sums + t;
@@ -430,6 +431,7 @@ int srcfd_slab_configure(srcfd_handle* h, int world, int rank, int nx_global, in
     S->guess[2] = h->p.inner_max;
     if (const char* e = getenv("SRCFD_SLAB_BLOCK")) S->block_cap = atoi(e);
     if (const char* e = getenv("SRCFD_SLAB_FOUR_FACES")) S->four_faces = atoi(e) != 0;
+    if (const char* e = getenv("SRCFD_JTB2_NL")) S->stream_nl = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("SRCFD_JTB2_FORCE")) { S->force_stream = atoi(e) != 0; if (S->force_stream) S->use_tiles = false; }   // no probe solve either
     S->mail_bytes = slab_mail_bytes(std::max(1, S->halo), h->K.pitch);
     auto bail = [&](int rc) { std::string keep = g_err; slab_release(h); g_err = keep; return rc; };
