@@ -241,7 +241,8 @@ __global__ void k_sr_post(float* __restrict__ y, const double* __restrict__ stat
     }
 }
 
-struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; __nv_bfloat16* Wlo = nullptr; };   // Wlo = bf16(W - Wbf): split-operand path
+struct Layer { float* W = nullptr; float* b = nullptr; __nv_bfloat16* Wbf = nullptr; __nv_bfloat16* Wlo = nullptr;   // Wlo = bf16(W - Wbf): split-operand path
+               __nv_bfloat16* Wimg = nullptr; };   // 3x3 ConvT only: both halves as the shared-memory image of k_convT3x3_l1_tc3's stages
 
 }  // namespace
 
@@ -264,6 +265,7 @@ struct srcfd_sr {
                                        // tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM)
     int tail_fused = 1;                // SRCFD_TAIL_FUSED=0: split-operand path with the last ConvT and the final conv as two launches
     int tail_fused_default = 1;
+    int l1_one_cta = 1, l1_one_cta_default = 1;   // SRCFD_L1_ONE_CTA=0: split-operand 3x3 ConvT as per-tap tiles (k_convT2x2_tc3) instead of k_convT3x3_l1_tc3
     int tc3_l1_ctas = 16;              // SRCFD_TC3_L1_CTAS: CTAs per tap of the split-operand 3x3 ConvT (9 taps x 16 = 144 CTAs on 148 SMs)
     int final_tc = 1;                  // SRCFD_FINAL_TC=0: final conv on the CUDA-core tile kernel
     int final_tc_rows = 8;             // SRCFD_FINAL_TC_ROWS: 4 | 8 | 16 output rows per CTA of the tensor-core final conv
@@ -385,6 +387,13 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
         // split-operand tensor-core path: fp32 activations end to end, every ConvT on tcgen05 as three bf16 MMAs per K-step
         {
             const long long M = (long long)B * 144;
+            if (h->l1_one_cta) {
+                // one CTA per 128-row tile: A staged once, the nine taps' weights streamed by the TMA engine
+                const size_t smem = srtc::l1_smem();
+                static bool attr1_done[64] = {false};
+                if (!attr1_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT3x3_l1_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1_done[h->dev & 63] = true; }
+                srtc::k_convT3x3_l1_tc3<<<(unsigned)((M + 127) / 128), 128, smem, h->stream>>>(h->act[0], h->dec[1].Wimg, h->act[5], M, h->tc_err);
+            } else {
             const size_t smem = srtc::convT_tc3_smem<256, 128, 2>();
             static bool attr_done[64] = {false};
             if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<256, 128, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
@@ -392,6 +401,7 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
             const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((M + 127) / 128, h->tc3_l1_ctas));
             srtc::k_convT2x2_tc3<256, 128, 1, 2><<<dim3(gx, 9), 128, smem, h->stream>>>(
                 h->act[0], h->dec[1].Wbf, h->dec[1].Wlo, h->dec[1].b, nullptr, M, 12, 12, h->tc_err, h->act[5], 1152);
+            }
             srtc::k_col2im_3x3s2_f32<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->act[1], B);
             h->launches += 2;
         }
@@ -467,6 +477,7 @@ int srcfd_sr_create(int device, srcfd_sr** out) {
     if (const char* e = getenv("SRCFD_FINAL_TC")) h->final_tc = atoi(e);
     if (const char* e = getenv("SRCFD_TAIL_FUSED")) h->tail_fused = h->tail_fused_default = atoi(e);
     if (const char* e = getenv("SRCFD_TC3_L1_CTAS")) h->tc3_l1_ctas = std::max(1, atoi(e));
+    if (const char* e = getenv("SRCFD_L1_ONE_CTA")) h->l1_one_cta = h->l1_one_cta_default = atoi(e);
     if (const char* e = getenv("SRCFD_FINAL_TC_ROWS")) h->final_tc_rows = atoi(e);
     *out = h;
     return SRCFD_OK;
@@ -477,7 +488,7 @@ int srcfd_sr_destroy(srcfd_sr* h) {
     cudaSetDevice(h->dev);
     cudaStreamSynchronize(h->stream);
     for (auto& l : h->enc) { cudaFree(l.W); cudaFree(l.b); }
-    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); cudaFree(l.Wlo); }
+    for (auto& l : h->dec) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wbf); cudaFree(l.Wlo); cudaFree(l.Wimg); }
     for (int i = 0; i < 6; ++i) cudaFree(h->actbf[i]);
     cudaFree(h->tc_err); cudaFree(h->stats_dev);
     for (int i = 0; i < 8; ++i) cudaFree(h->act[i]);
@@ -526,6 +537,18 @@ int srcfd_sr_set_decoder(srcfd_sr* h, const float* const kernels[7], const float
             if (!h->dec[l + 1].Wlo) SRCK(cudaMalloc(&h->dec[l + 1].Wlo, n * sizeof(__nv_bfloat16)));
             SRCK(cudaMemcpy(h->dec[l + 1].Wbf, wb.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
             SRCK(cudaMemcpy(h->dec[l + 1].Wlo, wl.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            if (l == 0) {     // the 3x3 layer's weights once more, laid out as the stages the TMA engine copies (sr_tc.cuh)
+                std::vector<__nv_bfloat16> img(2 * n);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int nn = 0; nn < 128; ++nn)
+                        for (int k = 0; k < 256; ++k) {
+                            const size_t src = ((size_t)tap * 128 + nn) * 256 + k;
+                            img[srtc::l1_img_index(tap, nn, k, 0)] = wb[src];
+                            img[srtc::l1_img_index(tap, nn, k, 1)] = wl[src];
+                        }
+                if (!h->dec[1].Wimg) SRCK(cudaMalloc(&h->dec[1].Wimg, img.size() * sizeof(__nv_bfloat16)));
+                SRCK(cudaMemcpy(h->dec[1].Wimg, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            }
         }
     }
     if (int rc = upload(&h->dec[6].W, kernels[6], 3 * 3 * 8 * 1, h->stream)) return rc;
@@ -634,8 +657,8 @@ int srcfd_sr_decode_device(srcfd_sr* h, uint64_t z_dev, int B, uint64_t out_dev,
 int srcfd_sr_set_precision(srcfd_sr* h, int mode) {
     if (!h || mode < 0 || mode > 4) return sr_fail(SRCFD_ERR_ARG, "bad argument");
     h->precision = mode == 0 ? 0 : mode >= 3 ? 3 : 1;
-    if (mode == 3) h->tail_fused = h->tail_fused_default; // mode 4: split-operand path with the last ConvT and the final conv as two launches (parity tests)
-    if (mode == 4) h->tail_fused = 0;
+    if (mode == 3) { h->tail_fused = h->tail_fused_default; h->l1_one_cta = h->l1_one_cta_default; }
+    if (mode == 4) { h->tail_fused = 0; h->l1_one_cta = 0; }   // the round-1 kernels for the 3x3 ConvT and the tail (same bits; parity tests)
     if (mode == 1) h->final_tc = 1;        // mode 2: bf16 layers with the final conv on the CUDA-core tile kernel (parity tests)
     if (mode == 2) h->final_tc = 0;
     return SRCFD_OK;

@@ -688,4 +688,155 @@ __global__ void __launch_bounds__(128) k_tail_fused_tc3(const float* __restrict_
     }
 }
 
+// ---- the 3x3 / stride-2 ConvT of the split-operand decoder as ONE CTA per 128-row tile (round 2) -----------------------
+// (sr-ae-conv.ipynb cell 277-287, conv2d_transpose 256 -> 128.)  Overlapping taps: nine per-tap GEMMs Y[m, tap, :] = A[m, :] W[tap]^T
+// (K = 256, N = 128), summed by k_col2im_3x3s2_f32.  As nine launches' worth of k_convT2x2_tc3 tiles every tap re-staged (and
+// re-split) the same 128 KB A tile and its own 128 KB of weights.  Here the A tile is staged and split ONCE (2 x 64 KB, resident)
+// and the weights STREAM through a two-deep ring of 32 KB stages (one quarter of K for both bf16 halves) filled by the TMA
+// engine: the host lays the split weights out once, at upload, as the exact shared-memory image of every stage (canonical
+// K-major core matrices), so a stage is one cp.async.bulk with an mbarrier transaction count.  One thread issues copies and
+// MMAs: wait full[s] -> 12 tcgen05.mma (4 K-steps x 3 split products) -> tcgen05.commit -> empty[s]; the copy of stage i+1
+// goes out as soon as stage i-1's MMAs have released its buffer, so copies run under the MMAs.  After a tap's fourth stage a
+// second commit signals the accumulator; all four warps drain it (tcgen05.ld) to Y while the next tap's first stages land.
+constexpr int L1_K = 256, L1_N = 128, L1_TAPS = 9, L1_Q = 4, L1_KQ = L1_K / L1_Q;          // 64 K per stage
+constexpr uint32_t L1_HALF_BYTES = L1_N * L1_KQ * 2, L1_STAGE_BYTES = 2 * L1_HALF_BYTES;   // 16 KB per bf16 half, 32 KB per stage
+constexpr size_t L1_A_BYTES = (size_t)128 * L1_K * 2;                                      // 64 KB per bf16 half of the A tile
+constexpr size_t l1_smem() { return 2 * L1_A_BYTES + 2 * (size_t)L1_STAGE_BYTES; }          // 192 KB
+// element index of weight (tap, n, k), bf16 half `half`, in the staged image
+__host__ __device__ inline size_t l1_img_index(int tap, int n, int k, int half) {
+    const int q = k / L1_KQ, kc = (k % L1_KQ) / 8, kk = k % 8;
+    return ((size_t)((tap * L1_Q + q) * 2 + half)) * (L1_HALF_BYTES / 2) + (size_t)kc * (L1_N / 8) * 64 + (size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8 + kk;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 20) && !done; ++spin)     // <= ~1 us per try: a lost arrival costs about a second, never a hang
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
+    return done != 0;
+}
+
+__global__ void __launch_bounds__(128) k_convT3x3_l1_tc3(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Wimg,
+                                                          float* __restrict__ Y, long long M, int* err) {
+    constexpr uint32_t LBO_A = (128 / 8) * 128, LBO_B = (L1_N / 8) * 128, SBO = 128;
+    constexpr int NST = L1_TAPS * L1_Q;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sAh = smem_raw;
+    unsigned char* sAl = smem_raw + L1_A_BYTES;
+    unsigned char* sW = smem_raw + 2 * L1_A_BYTES;            // two stages
+    __shared__ __align__(8) unsigned long long bars[5];       // full[2], empty[2], acc
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * 128;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), accb = smem_u32(&bars[4]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first two weight stages are on their way while the A tile is staged
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * i), "r"(L1_STAGE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sW + (size_t)i * L1_STAGE_BYTES)), "l"(Wimg + (size_t)i * (L1_STAGE_BYTES / 2)), "r"(L1_STAGE_BYTES), "r"(full0 + 8u * i) : "memory");
+        }
+    }
+    // ---- the A tile: 128 rows x 32 chunks of 8 floats, split into its bf16 halves (row fastest: conflict-free stores)
+#pragma unroll 1
+    for (int it = 0; it < 32; it += 4) {
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + (it + u) * 128, kc = c >> 7, r = c & 127;
+            va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u];
+            if (m0 + r < M) {
+                const float4* src = reinterpret_cast<const float4*>(A + (m0 + r) * L1_K + kc * 8);
+                va[u] = __ldg(src); vb[u] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = tid + (it + u) * 128, kc = c >> 7, r = c & 127;
+            const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const size_t so = (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(sAh + so) = hi;
+            *reinterpret_cast<uint4*>(sAl + so) = lo;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const long long m = m0 + warp * 32 + lane;
+    const bool valid = m < M;
+    bool dead = false, dead0 = false;
+#pragma unroll 1
+    for (int tap = 0; tap < L1_TAPS; ++tap) {
+        if (tid == 0 && !dead0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, L1_N);
+            const uint32_t ah = smem_u32(sAh), al = smem_u32(sAl);
+#pragma unroll 1
+            for (int q = 0; q < L1_Q; ++q) {
+                const int i = tap * L1_Q + q, sidx = i & 1;
+                if (!mbar_wait(full0 + 8u * sidx, (uint32_t)(i >> 1) & 1u)) { dead0 = true; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t wh = smem_u32(sW + (size_t)sidx * L1_STAGE_BYTES), wl = wh + L1_HALF_BYTES;
+#pragma unroll
+                for (int k = 0; k < L1_KQ / 16; ++k) {
+                    const uint32_t ao = (uint32_t)(q * (L1_KQ / 8) + 2 * k) * LBO_A, bo = (uint32_t)(2 * k) * LBO_B;
+                    const uint64_t adh = make_smem_desc(ah + ao, LBO_A, SBO), adl = make_smem_desc(al + ao, LBO_A, SBO);
+                    const uint64_t bdh = make_smem_desc(wh + bo, LBO_B, SBO), bdl = make_smem_desc(wl + bo, LBO_B, SBO);
+                    umma_bf16(tmem, adh, bdh, idesc, (q > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem, adh, bdl, idesc, 1u);
+                    umma_bf16(tmem, adl, bdh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8u * sidx) : "memory");
+                if (q == L1_Q - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accb) : "memory");
+                // refill: stage i+1 goes into the buffer stage i-1 used, once that stage's MMAs have completed
+                if (i >= 1 && i + 1 < NST) {
+                    const int pidx = (i - 1) & 1;
+                    if (!mbar_wait(empty0 + 8u * pidx, (uint32_t)((i - 1) >> 1) & 1u)) { dead0 = true; break; }
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * pidx), "r"(L1_STAGE_BYTES) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(sW + (size_t)pidx * L1_STAGE_BYTES)), "l"(Wimg + (size_t)(i + 1) * (L1_STAGE_BYTES / 2)), "r"(L1_STAGE_BYTES), "r"(full0 + 8u * pidx) : "memory");
+                }
+            }
+        }
+        if (!mbar_wait(accb, (uint32_t)tap & 1u)) { if (lane == 0) atomicExch(err, 1); dead = true; }
+        dead = __syncthreads_or(dead ? 1 : 0) != 0;
+        if (dead) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < L1_N; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(Y + m * (L1_TAPS * L1_N) + (long long)tap * L1_N + c0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                      // the accumulator is drained: the next tap may overwrite it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128) : "memory");
+}
+
 }  // namespace srtc
