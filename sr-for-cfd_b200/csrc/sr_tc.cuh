@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc(const __nv_bfloat16* __rest
         const long long m0 = tile * MT;
         // ---- stage A (zero rows past M)
         for (int c = tid; c < MT * KC; c += 128) {
-            const int r = c / KC, kc = c - r * KC;
+            const int kc = c / MT, r = c - kc * MT;               // row fastest: consecutive lanes store consecutive 16-byte core-matrix rows (no bank conflicts)
             uint4 v = make_uint4(0, 0, 0, 0);
             if (m0 + r < M) v = *reinterpret_cast<const uint4*>(A + (m0 + r) * KD + kc * 8);
             *reinterpret_cast<uint4*>(sA + (size_t)kc * LBO_A + (r >> 3) * SBO + (r & 7) * 16) = v;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
         for (int part = 0; part < KPART && !dead; ++part, phase ^= 1u) {
             // ---- stage this K-part of the A tile, split into its two bf16 halves (zero rows past M)
             for (int c = tid; c < MT * KCP; c += 128) {
-                const int r = c / KCP, kc = c - r * KCP;
+                const int kc = c / MT, r = c - kc * MT;           // row fastest: conflict-free shared-memory stores (kc fastest: all lanes on one bank)
                 float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (m0 + r < M) {
                     const float4* src = reinterpret_cast<const float4*>(A + (m0 + r) * KD + part * KP + kc * 8);

@@ -1,7 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_sr.py -q -x > gpurun_out/c16_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/c16_tests.log
-tail -12 gpurun_out/c16_tests.log
-timeout 300 python tools/bench_decoder.py > gpurun_out/c16_dec.json 2> gpurun_out/c16_dec.err; echo "dec rc=$?"
+timeout 300 python -m pytest tests/test_gpu_sr.py -q -x > gpurun_out/c19_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/c19_tests.log
+tail -12 gpurun_out/c19_tests.log
+timeout 300 python tools/bench_decoder.py > gpurun_out/c19_dec.json 2> gpurun_out/c19_dec.err; echo "dec rc=$?"
 python -c "
-import json; d=json.load(open('gpurun_out/c16_dec.json')); print({k:round(v['ms'],3) for k,v in d['paths'].items()}, d['tc_error'])"
+import json; d=json.load(open('gpurun_out/c19_dec.json')); print({k:round(v['ms'],3) for k,v in d['paths'].items()}, d['tc_error'])"
