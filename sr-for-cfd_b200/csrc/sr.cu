@@ -265,6 +265,7 @@ struct srcfd_sr {
                                        // tile per CTA, 8.01 ms persistent, 20.6 ms with ONE persistent CTA per SM)
     int tail_fused = 1;                // SRCFD_TAIL_FUSED=0: split-operand path with the last ConvT and the final conv as two launches
     int tail_fused_default = 1;
+    int tc3_wide256 = 1;               // SRCFD_TC3_WIDE256=0: the 128->64 and 64->32 split-operand layers with 128 threads per CTA
     int l1_one_cta = 1, l1_one_cta_default = 1;   // SRCFD_L1_ONE_CTA=0: split-operand 3x3 ConvT as per-tap tiles (k_convT2x2_tc3) instead of k_convT3x3_l1_tc3
     int tc3_l1_ctas = 16;              // SRCFD_TC3_L1_CTAS: CTAs per tap of the split-operand 3x3 ConvT (9 taps x 16 = 144 CTAs on 148 SMs)
     int final_tc = 1;                  // SRCFD_FINAL_TC=0: final conv on the CUDA-core tile kernel
@@ -338,18 +339,19 @@ int launch_convT_tc(srcfd_sr* h, const __nv_bfloat16* in, const __nv_bfloat16* W
     return SRCFD_OK;
 }
 // split-operand (bf16 x 3) ConvT layer: fp32 activation in and out
-template <int KD, int ND>
+template <int KD, int ND, int NTv = 128>
 int launch_convT_tc3(srcfd_sr* h, const float* in, const Layer& L, float* out, int B, int H) {
     const long long M = (long long)B * H * H;
     const size_t smem = srtc::convT_tc3_smem<KD, ND, 1>();
+    constexpr int NT = NTv;
     static bool attr_done[64] = {false};
-    if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<KD, ND, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
+    if (!attr_done[h->dev & 63]) { SRCK(cudaFuncSetAttribute(srtc::k_convT2x2_tc3<KD, ND, 0, 1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->dev & 63] = true; }
     static int sms_dev[64] = {0};
     if (!sms_dev[h->dev & 63]) SRCK(cudaDeviceGetAttribute(&sms_dev[h->dev & 63], cudaDevAttrMultiProcessorCount, h->dev));
     const long long ntiles = (M + 127) / 128;
     const int per_sm = std::max(1, std::min(std::min(h->tc_persist, 512 / (ND < 32 ? 32 : ND)), (int)((size_t)220 * 1024 / smem)));
     const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)per_sm * sms_dev[h->dev & 63]);
-    srtc::k_convT2x2_tc3<KD, ND, 0, 1><<<grid, 128, smem, h->stream>>>(in, L.Wbf, L.Wlo, L.b, out, M, H, H, h->tc_err);
+    srtc::k_convT2x2_tc3<KD, ND, 0, 1, NT><<<grid, NT, smem, h->stream>>>(in, L.Wbf, L.Wlo, L.b, out, M, H, H, h->tc_err);
     h->launches += 1;
     SRCK(cudaGetLastError());
     return SRCFD_OK;
@@ -405,8 +407,13 @@ int run_decoder(srcfd_sr* h, const float* z_dev, int B, float* out_dev) {
             srtc::k_col2im_3x3s2_f32<<<nblk((long long)B * 25 * 25 * 128), 256, 0, h->stream>>>(h->act[5], h->dec[1].b, h->act[1], B);
             h->launches += 2;
         }
-        if (int rc = launch_convT_tc3<128, 256>(h, h->act[1], h->dec[2], h->act[2], B, 25)) return rc;
-        if (int rc = launch_convT_tc3<64, 128>(h, h->act[2], h->dec[3], h->act[3], B, 50)) return rc;
+        if (h->tc3_wide256) {      // 256 threads: a second warpgroup for staging and for half of each accumulator row's columns
+            if (int rc = launch_convT_tc3<128, 256, 256>(h, h->act[1], h->dec[2], h->act[2], B, 25)) return rc;
+            if (int rc = launch_convT_tc3<64, 128, 256>(h, h->act[2], h->dec[3], h->act[3], B, 50)) return rc;
+        } else {
+            if (int rc = launch_convT_tc3<128, 256>(h, h->act[1], h->dec[2], h->act[2], B, 25)) return rc;
+            if (int rc = launch_convT_tc3<64, 128>(h, h->act[2], h->dec[3], h->act[3], B, 50)) return rc;
+        }
         if (int rc = launch_convT_tc3<32, 64>(h, h->act[3], h->dec[4], h->act[4], B, 100)) return rc;
         if (h->tail_fused) {
             // last ConvT + final conv in one kernel: the (B, 400, 400, 8) activation between them stays in shared memory
@@ -477,6 +484,7 @@ int srcfd_sr_create(int device, srcfd_sr** out) {
     if (const char* e = getenv("SRCFD_FINAL_TC")) h->final_tc = atoi(e);
     if (const char* e = getenv("SRCFD_TAIL_FUSED")) h->tail_fused = h->tail_fused_default = atoi(e);
     if (const char* e = getenv("SRCFD_TC3_L1_CTAS")) h->tc3_l1_ctas = std::max(1, atoi(e));
+    if (const char* e = getenv("SRCFD_TC3_WIDE256")) h->tc3_wide256 = atoi(e);
     if (const char* e = getenv("SRCFD_L1_ONE_CTA")) h->l1_one_cta = h->l1_one_cta_default = atoi(e);
     if (const char* e = getenv("SRCFD_FINAL_TC_ROWS")) h->final_tc_rows = atoi(e);
     *out = h;

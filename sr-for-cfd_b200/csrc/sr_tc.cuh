@@ -204,8 +204,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     }
     hi = *reinterpret_cast<const uint4*>(h); lo = *reinterpret_cast<const uint4*>(l);
 }
-template <int KD, int ND, int EPI, int KPART>
-__global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Whi,
+// NT = 128 or 256 threads: with 256 the second warpgroup shares the staging and takes the upper half of every accumulator row's
+// columns in the epilogue (a warp reads the TMEM lane quarter warp % 4), for the wide layers that fit one or three CTAs per SM.
+template <int KD, int ND, int EPI, int KPART, int NT = 128>
+__global__ void __launch_bounds__(NT) k_convT2x2_tc3(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Whi,
                                                        const __nv_bfloat16* __restrict__ Wlo, const float* __restrict__ bias,
                                                        float* __restrict__ out, long long M, int H, int Wd, int* err,
                                                        float* __restrict__ Y = nullptr, int ldy = 0) {
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_bias[COUT];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (EPI == 0) for (int c = tid; c < COUT; c += 128) s_bias[c] = bias[c];
+    const int wq = warp & 3, whalf = warp >> 2;             // TMEM lane quarter / column half of this warp
+    if (EPI == 0) for (int c = tid; c < COUT; c += NT) s_bias[c] = bias[c];
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(ND < 32 ? 32 : ND) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int c = tid; c < ND * KC; c += 128) {                   // both halves of the weights, once per CTA
+    for (int c = tid; c < ND * KC; c += NT) {                    // both halves of the weights, once per CTA
         const int n = c / KC, kc = c - n * KC;
         const size_t so = (size_t)kc * LBO_B + (n >> 3) * SBO + (n & 7) * 16;
         *reinterpret_cast<uint4*>(sBh + so) = *reinterpret_cast<const uint4*>(Whi + (size_t)n * KD + kc * 8);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
 #pragma unroll 1
         for (int part = 0; part < KPART && !dead; ++part, phase ^= 1u) {
             // ---- stage this K-part of the A tile, split into its two bf16 halves (zero rows past M)
-            for (int c = tid; c < MT * KCP; c += 128) {
+            for (int c = tid; c < MT * KCP; c += NT) {
                 const int kc = c / MT, r = c - kc * MT;           // row fastest: conflict-free shared-memory stores (kc fastest: all lanes on one bank)
                 float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (m0 + r < M) {
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
         }
         if (dead) break;
         // ---- epilogue: thread = accumulator row (TMEM lane) 32*warp + lane
-        const long long m = m0 + warp * 32 + lane;
+        const long long m = m0 + wq * 32 + lane;
         const bool valid = m < M;
         long long pix = valid ? m : 0;
         const int x = (int)(pix % Wd); pix /= Wd;
@@ -300,9 +303,9 @@ __global__ void __launch_bounds__(128) k_convT2x2_tc3(const float* __restrict__ 
         const long long b = pix / H;
         const uint32_t tmem = tmem_base_s;
 #pragma unroll 1
-        for (int c0 = 0; c0 < ND; c0 += 16) {
+        for (int c0 = whalf * (ND / (NT / 128)); c0 < (whalf + 1) * (ND / (NT / 128)); c0 += 16) {
             uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
