@@ -396,7 +396,7 @@ static int slab_implicit_solve(SlabGroup& G) {
         SlabState* S = h->slab;
         k_correct_velocity<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, h->res_partials, h->K, h->ctrl, S->own0, S->own1);
         LAUNCH_CHECK(h);
-        k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl, S->sums);
+        k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl, S->sums, 0);
         LAUNCH_CHECK(h);
         return SRCFD_OK;
     }));

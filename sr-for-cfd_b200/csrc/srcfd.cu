@@ -527,10 +527,10 @@ static int l_copy_new_to_old(srcfd_handle* h) {
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
-static int l_apply_bc(srcfd_handle* h, int k, int mode = 0) {
+static int l_apply_bc(srcfd_handle* h, int k, int mode = 0, int nk = 1) {
     h->jtb_ghosts_valid = false;
     const int n = std::max(h->K.nx, h->K.ny);
-    k_apply_bc<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Var, k, h->K, h->bc, mode, h->ctrl);
+    k_apply_bc<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Var, k, h->K, h->bc, mode, h->ctrl, nk);
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
@@ -550,15 +550,15 @@ static int l_update_flux(srcfd_handle* h) {
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
-static int l_under_relax(srcfd_handle* h, int k, double alpha) {
-    k_under_relax<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, k, alpha, h->K, h->ctrl);
+static int l_under_relax(srcfd_handle* h, int k, double alpha, int k2 = -1, double alpha2 = 1.0) {
+    k_under_relax<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, k, alpha, h->K, h->ctrl, k2, alpha2);
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
-static int l_correct_velocity(srcfd_handle* h) {
+static int l_correct_velocity(srcfd_handle* h, bool assign = false) {
     k_correct_velocity<<<h->tail_blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, h->res_partials, h->K, h->ctrl, 1, h->K.nx);
     LAUNCH_CHECK(h);
-    k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl, nullptr);
+    k_residual_finish<<<1, 256, 0, h->stream>>>(h->res_partials, h->tail_blocks, h->ctrl, nullptr, assign ? 1 : 0);
     LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
@@ -567,11 +567,6 @@ static int l_clear_stop(srcfd_handle* h) {
     k_clear_stop<<<1, 1, 0, h->stream>>>(h->ctrl);
     LAUNCH_CHECK(h);
     h->maybe_stopped = false;
-    return SRCFD_OK;
-}
-static int l_zero_residual(srcfd_handle* h) {
-    k_zero_residual<<<1, 1, 0, h->stream>>>(h->ctrl);
-    LAUNCH_CHECK(h);
     return SRCFD_OK;
 }
 
@@ -702,7 +697,7 @@ static int l_inner_solve(srcfd_handle* h, int op, int k, int slot, bool pair = f
 
 // _implicit_solve: LDC.py:432-467 / BFS.py:622-673
 static int l_implicit_solve(srcfd_handle* h) {
-    TRY(l_zero_residual(h));
+    // (the residual sums are ASSIGNED by k_residual_finish below, which is what zeroing them here and adding there amounts to)
     const int mop = h->p.scheme == SRCFD_SCHEME_QUICK ? OP_QUICK : OP_UPWIND;
     // The u and v momentum solves are independent (different planes, same read-only Ff): one paired wavefront
     // launch when the reference order is in use.  The BFS inlet pass for k = 0 also rewrites the v ghost column
@@ -714,10 +709,11 @@ static int l_implicit_solve(srcfd_handle* h) {
     if (pair) {
         if (h->bc.bfs && !h->ghosts_fresh) TRY(l_apply_bc(h, 0, 4));
         TRY(l_inner_solve(h, mop, 0, 0, true));
-        for (int k = 0; k < 2; ++k) {
-            if (h->p.relax_enabled) TRY(l_under_relax(h, k, h->p.relax[k]));
-            TRY(l_apply_bc(h, k));
-        }
+        // relax u, BC u, relax v, BC v as two launches: the relaxations touch interior cells of their own plane only, and the one
+        // cross-plane write of the BC passes (the k = 0 inlet pass resets the v ghost column, BFS.py:562) is overwritten by the
+        // k = 1 pass that follows it in the same thread
+        if (h->p.relax_enabled) TRY(l_under_relax(h, 0, h->p.relax[0], 1, h->p.relax[1]));
+        TRY(l_apply_bc(h, 0, 0, 2));
     } else {
         for (int k = 0; k < 2; ++k) {
             TRY(l_inner_solve(h, mop, k, k));
@@ -729,9 +725,8 @@ static int l_implicit_solve(srcfd_handle* h) {
     TRY(l_inner_solve(h, OP_PRESSURE, 2, 2));
     if (h->p.relax_enabled) TRY(l_under_relax(h, 2, h->p.relax[2]));
     TRY(l_apply_bc(h, 2));
-    TRY(l_correct_velocity(h));
-    TRY(l_apply_bc(h, 0));
-    TRY(l_apply_bc(h, 1));
+    TRY(l_correct_velocity(h, true));
+    TRY(l_apply_bc(h, 0, 0, 2));
     TRY(l_update_flux(h));
     h->ghosts_fresh = true;
     return SRCFD_OK;
@@ -796,9 +791,12 @@ int srcfd_step(srcfd_handle* h, int64_t n_outer, const double crit[3]) {
     h->maybe_stopped = true;
     for (int64_t it = 0; it < n_outer; ++it) {
         TRY(l_implicit_solve(h));
-        k_convergence_check<<<1, 1, 0, h->stream>>>(h->ctrl, h->hist, h->K, crit[0], crit[1], crit[2]);
-        LAUNCH_CHECK(h);
-        TRY(l_copy_new_to_old(h));
+        {   // _convergence_check + copy_new_to_old in one launch
+            const long long n = 3 * h->K.plane;
+            const int blocks = (int)std::min<long long>((n + TAIL_THREADS - 1) / TAIL_THREADS, (long long)h->num_sms * 8);
+            k_check_and_copy<<<blocks, TAIL_THREADS, 0, h->stream>>>(h->Var, h->VarOld, n, h->ctrl, h->hist, h->K, crit[0], crit[1], crit[2]);
+            LAUNCH_CHECK(h);
+        }
     }
     return SRCFD_OK;
 }

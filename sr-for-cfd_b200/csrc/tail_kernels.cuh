@@ -28,10 +28,13 @@ __global__ void k_copy_new_to_old(const double* __restrict__ Var, double* __rest
 // _apply_bc_wrapper: apply_bc_configured (LDC.py:117-145) then _apply_bfs_inlet (BFS.py:524-562).
 // One thread per boundary index t in [1, max(nx,ny)]; corners are never written.
 // mode: 0 = both (the wrapper), 1 = apply_bc_configured only, 2 = _apply_bfs_inlet only.
-__global__ void k_apply_bc(double* __restrict__ Var, int k, Consts K, BcSpec bc, int mode, const Ctrl* ctrl) {
+// nk > 1: planes k .. k+nk-1 in ONE launch, each thread taking its boundary index through the planes in order -- every cell
+// a pass touches belongs to its own index (corners are never written), so this is the sequence of separate launches.
+__global__ void k_apply_bc(double* __restrict__ Var, int k0, Consts K, BcSpec bc, int mode, const Ctrl* ctrl, int nk) {
     if (ctrl->stop) return;
-    const bool generic = (mode != 2), inlet = (mode != 1) && bc.bfs && (k == 0 || k == 1) && !bc.skip_lo;
     const int t = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  for (int k = k0; k < k0 + nk; ++k) {
+    const bool generic = (mode != 2), inlet = (mode != 1) && bc.bfs && (k == 0 || k == 1) && !bc.skip_lo;
     double* V = Var + (long long)k * K.plane;
     if (mode == 4) {
         // only the side effect of the k = 0 inlet pass on the v ghost column (BFS.py:562), so that a paired u/v solve
@@ -77,6 +80,7 @@ __global__ void k_apply_bc(double* __restrict__ Var, int k, Consts K, BcSpec bc,
         if (bc.types[k][3] == 0) V[row] = 2 * bc.values[k][3] - V[row + 1];
         else                     V[row] = V[row + 1];
     }
+  }
 }
 
 // LDC.py:147-154 linear_interpolation; also emits rhs = rho/dt*(fE+fN+fW+fS) (LDC.py:305) when rhs != null,
@@ -117,13 +121,18 @@ __global__ void k_update_flux(const double* __restrict__ Var, double* __restrict
 }
 
 // BFS.py:371-375 under_relax_field
+// k2 >= 0: plane k2 with factor alpha2 in the same launch (u and v after a paired momentum solve)
 __global__ void k_under_relax(double* __restrict__ Var, const double* __restrict__ VarOld, int k, double alpha,
-                              Consts K, const Ctrl* ctrl) {
+                              Consts K, const Ctrl* ctrl, int k2, double alpha2) {
     if (ctrl->stop) return;
     int i, j; long long c;
     if (!cell_of_thread(K, i, j, c)) return;
     const long long o = (long long)k * K.plane + c;
     Var[o] = VarOld[o] + alpha * (Var[o] - VarOld[o]);
+    if (k2 >= 0) {
+        const long long o2 = (long long)k2 * K.plane + c;
+        Var[o2] = VarOld[o2] + alpha2 * (Var[o2] - VarOld[o2]);
+    }
 }
 
 // LDC.py:316-328 correct_velocity.  Residual sums: per-block partials in a fixed order, finished by
@@ -153,14 +162,16 @@ __global__ void k_correct_velocity(double* __restrict__ Var, const double* __res
 
 // residual[k] += sum of partials (fixed order: strided lanes, then block_sum).  One block.
 // out != null: the three sums go there instead (a slab hands them to the exchange that adds the ranks up).
-__global__ void k_residual_finish(const double* __restrict__ partials, int nblocks, Ctrl* ctrl, double* __restrict__ out) {
+// assign: residual[k] = tot (the composed iteration: the reference zeroes the array at the top of _implicit_solve and nothing
+// else adds to it, and 0.0 + tot == tot) -- saves the zeroing launch.
+__global__ void k_residual_finish(const double* __restrict__ partials, int nblocks, Ctrl* ctrl, double* __restrict__ out, int assign) {
     if (ctrl->stop) return;
     __shared__ double scratch[32];
     for (int k = 0; k < 3; ++k) {
         double s = 0.0;
         for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[3 * b + k];
         const double tot = block_sum(s, scratch);
-        if (threadIdx.x == 0) { if (out) out[k] = tot; else ctrl->residual[k] += tot; }
+        if (threadIdx.x == 0) { if (out) out[k] = tot; else if (assign) ctrl->residual[k] = 0.0 + tot; else ctrl->residual[k] += tot; }
         __syncthreads();
     }
 }
@@ -169,10 +180,6 @@ __global__ void k_residual_finish(const double* __restrict__ partials, int nbloc
 // the next kernel-level or composed call starts from a clean verdict (the reference's methods always run).
 __global__ void k_clear_stop(Ctrl* ctrl) { ctrl->stop = 0; ctrl->converged = 0; ctrl->nan_flag = 0; }
 
-__global__ void k_zero_residual(Ctrl* ctrl) {
-    if (ctrl->stop) return;
-    ctrl->residual[0] = ctrl->residual[1] = ctrl->residual[2] = 0.0;
-}
 
 // _convergence_check (LDC.py:469-501) + the bookkeeping of solve() (LDC.py:408-419).  One thread.
 // The copy_new_to_old that follows is a separate launch that sees stop == 1 when converged.
@@ -197,6 +204,41 @@ __global__ void k_convergence_check(Ctrl* ctrl, double* hist, Consts K, double c
         ctrl->n_hist += 1;
     }
     if (converged) { ctrl->converged = 1; ctrl->stop = 1; }
+}
+
+// The verdict above and the copy_new_to_old that follows it in ONE launch (srcfd_step): every thread evaluates the verdict
+// from the three residual sums (a pure function of ctrl->residual and the criteria, the same operations as
+// k_convergence_check), copies only if the iteration neither converged nor failed, and thread 0 of block 0 does the
+// bookkeeping.  A block that starts after stop was raised returns at once -- the case in which nothing is copied anyway.
+__global__ void k_check_and_copy(const double* __restrict__ Var, double* __restrict__ VarOld, long long n, Ctrl* ctrl,
+                                 double* hist, Consts K, double cu, double cv, double cp) {
+    if (ctrl->stop) return;
+    double rms[3];
+    bool bad = false;
+    for (int k = 0; k < 3; ++k) {
+        rms[k] = sqrt(ctrl->residual[k] / (double)((long long)K.nx * (long long)K.ny));
+        rms[k] = rms[k] / K.dt;
+        if (isnan(rms[k]) || isinf(rms[k])) bad = true;
+    }
+    bool converged = true;
+    if (rms[0] > cu) converged = false;
+    if (rms[1] > cv) converged = false;
+    if (rms[2] > cp) converged = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) ctrl->rms[k] = rms[k];
+        ctrl->iterations += 1;
+        if (bad) { ctrl->nan_flag = 1; ctrl->stop = 1; }
+        else {
+            if (ctrl->iterations % 100 == 0 && hist && ctrl->n_hist < ctrl->hist_cap) {
+                hist[3 * ctrl->n_hist + 0] = rms[0]; hist[3 * ctrl->n_hist + 1] = rms[1]; hist[3 * ctrl->n_hist + 2] = rms[2];
+                ctrl->n_hist += 1;
+            }
+            if (converged) { ctrl->converged = 1; ctrl->stop = 1; }
+        }
+    }
+    if (bad || converged) return;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        VarOld[t] = Var[t];
 }
 
 // Warm-start injection (LDC.py:936-938): Var[k, 1:-1, 1:-1] = field_k.T with field_k of shape (ny, nx).
